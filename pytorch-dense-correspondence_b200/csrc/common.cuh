@@ -1,0 +1,73 @@
+// Shared helpers for libddn_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+
+#include "../../include/ddn_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libddn_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace ddn {
+
+extern std::atomic<long long> g_launches;
+void set_error(const char* fmt, ...);
+
+#define DDN_CHECK_ARG(cond, ...)                 \
+  do {                                           \
+    if (!(cond)) {                               \
+      ::ddn::set_error(__VA_ARGS__);             \
+      return DDN_EINVAL;                         \
+    }                                            \
+  } while (0)
+
+#define DDN_CUDA(call)                                                                  \
+  do {                                                                                  \
+    cudaError_t e__ = (call);                                                           \
+    if (e__ != cudaSuccess) {                                                           \
+      ::ddn::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return (int)e__;                                                                  \
+    }                                                                                   \
+  } while (0)
+
+#define DDN_TRY(call)          \
+  do {                         \
+    int r__ = (call);          \
+    if (r__ != 0) return r__;  \
+  } while (0)
+
+// Every kernel launch goes through this so gpu_launches is an honest count.
+#define DDN_LAUNCH(kernel, grid, block, smem, stream, ...)         \
+  do {                                                             \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);    \
+    ::ddn::g_launches.fetch_add(1, std::memory_order_relaxed);     \
+    DDN_CUDA(cudaGetLastError());                                  \
+  } while (0)
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+int num_sms();
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace ddn

@@ -1,0 +1,122 @@
+"""Data parallelism for the dense-descriptor training step: one process per GPU, independent image pairs per
+rank, and exactly one exchange per step -- an all-reduce (SUM, then 1/world) of the fp32 parameter gradients
+over NCCL / NVLink.  The reference itself is single-GPU (training.py:254-256); BatchNorm
+statistics stay per rank, as N independent reference processes would have them.
+
+Because every parameter (and therefore, after backward, every gradient) of ``Resnet34_8s`` aliases one flat
+fp32 array, the exchange is a handful of large bucketed all-reduces over slices of that array instead of
+110 small ones.  Works on CUDA (nccl) and, for the host-logic tests, on CPU tensors (gloo).
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """torchrun-style rendezvous from RANK / WORLD_SIZE / LOCAL_RANK / MASTER_ADDR / MASTER_PORT.
+    Returns (rank, world_size, local_rank).  A single process (no env) returns (0, 1, 0) without initialising."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local_rank
+
+
+def shard_range(global_count, rank, world):
+    """Consecutive split of ``global_count`` units over ``world`` ranks: -> (start, count).  The first
+    ``global_count % world`` ranks take one extra unit."""
+    base, extra = divmod(global_count, world)
+    count = base + (1 if rank < extra else 0)
+    start = rank * base + min(rank, extra)
+    return start, count
+
+
+def broadcast_parameters(module, src=0, group=None):
+    """Make every rank start from rank ``src``'s weights and BN buffers (one broadcast per flat array when the
+    module exposes them, else per tensor)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t.data, src=src, group=group)
+
+
+def _flat_view_of(tensors):
+    """If ``tensors`` tile one contiguous storage in order (gaps of < 16 bytes allowed), return
+    (base_tensor_1d covering all of them); else None."""
+    if not tensors:
+        return None
+    t0 = tensors[0]
+    if any(t.dtype != t0.dtype or t.device != t0.device or not t.is_contiguous() for t in tensors):
+        return None
+    es = t0.element_size()
+    storage_ptr = t0.untyped_storage().data_ptr()
+    if any(t.untyped_storage().data_ptr() != storage_ptr for t in tensors):
+        return None
+    cursor = t0.data_ptr()
+    for t in tensors:
+        gap = t.data_ptr() - cursor
+        if gap < 0 or gap >= 16:
+            return None
+        cursor = t.data_ptr() + t.numel() * es
+    start = (t0.data_ptr() - storage_ptr) // es
+    length = (cursor - t0.data_ptr()) // es
+    return torch.empty(0, dtype=t0.dtype, device=t0.device).set_(t0.untyped_storage(), start, (length,), (1,))
+
+
+class GradientAllReducer(object):
+    """Averages ``p.grad`` of the given parameters across the process group.
+
+        reducer = GradientAllReducer(dcn.parameters())
+        loss.backward(); reducer(); optimizer.step()
+    """
+
+    def __init__(self, parameters, group=None, num_buckets=4):
+        self.params = [p for p in parameters if p.requires_grad]
+        self.group = group
+        self.num_buckets = max(1, int(num_buckets))
+        self.bytes_last = 0
+        self.used_flat_path = False
+
+    def __call__(self):
+        if not dist.is_initialized():
+            return
+        world = dist.get_world_size(self.group)
+        if world == 1:
+            return
+        grads = [p.grad for p in self.params if p.grad is not None]
+        if not grads:
+            return
+        flat = _flat_view_of(grads)
+        self.used_flat_path = flat is not None
+        if flat is None:   # gradients are scattered: pack, reduce, unpack
+            flat = torch.cat([g.reshape(-1) for g in grads])
+        n = flat.numel()
+        self.bytes_last = n * flat.element_size()
+        # reverse order: the tail of the flat array (layer4, fc) is what backward finishes first
+        bounds = [n * i // self.num_buckets // 4 * 4 for i in range(self.num_buckets)] + [n]
+        works = []
+        for i in reversed(range(self.num_buckets)):
+            if bounds[i + 1] > bounds[i]:
+                works.append(dist.all_reduce(flat[bounds[i]:bounds[i + 1]], op=dist.ReduceOp.SUM, group=self.group,
+                                             async_op=True))
+        for w in works:
+            w.wait()
+        if flat.is_cuda:
+            from . import ops
+            ops.scale_inplace(flat, 1.0 / world)
+        else:
+            flat.mul_(1.0 / world)
+        if not self.used_flat_path:
+            off = 0
+            for g in grads:
+                g.copy_(flat[off:off + g.numel()].view_as(g))
+                off += g.numel()
