@@ -211,6 +211,19 @@ int ddn_upsample_bilinear_backward(const float* dy, float* dx, int NC, int h, in
 /* Data-parallel helpers on the flat gradient: g *= scale (after an all-reduce SUM over ranks). */
 int ddn_scale_inplace(float* g, int64_t n, float scale, void* stream);
 
+/* Per-kernel-class device timing (CUDA events recorded on the launching stream around each launch of the
+ * convolution / loss kernels while enabled).  ddn_profile_read synchronises on the recorded events and
+ * fills one entry per class that ran: work = algorithmic FLOPs (conv_*) or bytes (loss_*). */
+typedef struct {
+  char name[32];
+  int64_t launches;
+  double ms;
+  double work;
+} ddn_profile_entry;
+int ddn_profile_enable(int on);
+int ddn_profile_reset(void);
+int ddn_profile_read(ddn_profile_entry* out, int cap);
+
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t ddn_kernel_launch_count(void);
 

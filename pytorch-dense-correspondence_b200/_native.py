@@ -29,6 +29,10 @@ class LossTerm(ctypes.Structure):
                 ("kind", ctypes.c_int32), ("flags", ctypes.c_int32), ("margin", f32), ("m_pixel", f32)]
 
 
+class ProfileEntry(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char * 32), ("launches", ctypes.c_int64), ("ms", ctypes.c_double), ("work", ctypes.c_double)]
+
+
 class WithinSceneCfg(ctypes.Structure):
     _fields_ = [("match_loss_weight", f32), ("non_match_loss_weight", f32),
                 ("scale_by_hard_negatives", ctypes.c_int32), ("has_blind", ctypes.c_int32),
@@ -61,6 +65,9 @@ _SIGNATURES = {
     "ddn_upsample_bilinear_forward": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "ddn_upsample_bilinear_backward": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "ddn_scale_inplace": (i32, [vp, i64, f32, vp]),
+    "ddn_profile_enable": (i32, [i32]),
+    "ddn_profile_reset": (i32, []),
+    "ddn_profile_read": (i32, [ctypes.POINTER(ProfileEntry), i32]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -121,6 +128,17 @@ def buffer_table():
     arr = (TensorEntry * n)()
     lib.ddn_resnet34_8s_buffer_table(arr, n)
     return [(e.name.decode(), tuple(e.shape[:e.ndim]), int(e.offset), int(e.numel)) for e in arr]
+
+
+def profile_read():
+    """{class name: {"launches", "ms", "flops" (conv_*) or "bytes" (loss_*)}} for the kernels timed since the last reset."""
+    arr = (ProfileEntry * 16)()
+    n = lib.ddn_profile_read(arr, 16)
+    out = {}
+    for e in arr[:n]:
+        name = e.name.decode()
+        out[name] = {"launches": int(e.launches), "ms": float(e.ms), ("flops" if name.startswith("conv") else "bytes"): float(e.work)}
+    return out
 
 
 def launch_count():

@@ -38,8 +38,8 @@ def _as_index(idx, B, name):
         raise RuntimeError("%s must be a CUDA tensor" % name)
     if idx.dtype != torch.int64:
         raise RuntimeError("%s must be int64 (torch.LongTensor), got %s" % (name, idx.dtype))
-    if idx.dim() == 1:
-        idx = idx.unsqueeze(0)
+    if idx.dim() == 1:          # one index list shared by every pair of the batch (e.g. the [-1] sentinel)
+        idx = idx.unsqueeze(0).expand(B, -1)
     if idx.dim() != 2 or idx.shape[0] != B:
         raise RuntimeError("%s must have shape [n] or [B, n] with B=%d, got %s" % (name, B, tuple(idx.shape)))
     return idx.contiguous()

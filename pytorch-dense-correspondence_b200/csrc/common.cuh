@@ -54,6 +54,15 @@ static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; 
 
 int num_sms();
 
+// Optional per-kernel-class timing with CUDA events on the launching stream (off by default; bench.py turns it on).
+enum ProfClass { PROF_CONV_FWD_SIMT = 0, PROF_CONV_DGRAD_SIMT, PROF_CONV_WGRAD_SIMT, PROF_CONV_FWD_TC, PROF_CONV_DGRAD_TC,
+                 PROF_CONV_WGRAD_TC, PROF_LOSS_FWD, PROF_LOSS_BWD, PROF_NUM_CLASSES };
+struct ProfScope {
+  ProfScope(int cls, double work, cudaStream_t st);
+  ~ProfScope();
+  int slot; cudaStream_t st;
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

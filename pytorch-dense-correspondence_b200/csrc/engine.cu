@@ -34,6 +34,34 @@ int num_sms() {
   return n;
 }
 
+// ------------------------------------------------------------------------------------------------ profiler
+static const char* kProfNames[PROF_NUM_CLASSES] = {"conv_fwd_simt", "conv_dgrad_simt", "conv_wgrad_simt", "conv_fwd_tc",
+                                                   "conv_dgrad_tc", "conv_wgrad_tc", "loss_fwd", "loss_bwd"};
+struct ProfRec { int cls; double work; cudaEvent_t a, b; };
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+static size_t g_prof_used = 0;
+static std::atomic<int> g_prof_on{0};
+
+ProfScope::ProfScope(int cls, double work, cudaStream_t s) : slot(-1), st(s) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (g_prof_used == g_prof.size()) {
+    if (g_prof.size() >= (1u << 17)) return;
+    ProfRec r; r.cls = cls; r.work = work;
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    g_prof.push_back(r);
+  }
+  slot = (int)g_prof_used++;
+  g_prof[slot].cls = cls; g_prof[slot].work = work;
+  cudaEventRecord(g_prof[slot].a, st);
+}
+ProfScope::~ProfScope() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEventRecord(g_prof[slot].b, st);
+}
+
 // ------------------------------------------------------------------------------------------------ network description
 struct ConvSpec { int cin, cout, k, stride, pad, dil; int64_t w_off; };
 struct BnSpec { int C; int64_t g_off, b_off, rm_off, rv_off; };
@@ -211,13 +239,16 @@ struct Ctx {
 static int conv_forward(const Ctx& c, const ConvSpec& cs, const float* in, float* out, int N, int Hin, int Win, int Hout, int Wout,
                         int cin_eff) {
   const float* w = c.params + cs.w_off;
+  const double fl = 2.0 * N * Hout * Wout * (double)cs.cout * cs.k * cs.k * cs.cin;
   if (c.p->precision != DDN_PRECISION_FP32_SIMT && tc_conv_supported(cs.cin, cs.cout, cs.k, cs.stride, cs.pad, cs.dil, Hin, Win)) {
+    ProfScope ps(PROF_CONV_FWD_TC, fl, c.st);
     return tc_conv_forward(in, w, out, N, Hin, Win, cs.cin, cs.cout, cs.k, cs.pad, cs.dil, c.p->precision,
                            c.ws + c.p->tc, c.p->tc_bytes, c.st);
   }
   ConvGeom g;
   DDN_TRY(conv_geom_init(&g, N, Hin, Win, cin_eff, Hout, Wout, cs.cout, cs.k, cs.k, cs.stride, 1, cs.pad, cs.dil));
   DDN_TRY(launch_pack_weights(w, c.f(c.p->wpack), cs.cout, cs.cin, cin_eff, cs.k, cs.k, 0, c.st));
+  ProfScope ps(PROF_CONV_FWD_SIMT, fl, c.st);
   return launch_conv_gather_f32(in, c.f(c.p->wpack), nullptr, out, g, c.st);
 }
 
@@ -272,6 +303,7 @@ static int conv_backward(const Ctx& c, const ConvSpec& cs, const float* in, cons
   const Plan& p = *c.p;
   const float* w = c.params + cs.w_off;
   float* dw = c.grads + cs.w_off;
+  const double fl = 2.0 * N * Hout * Wout * (double)cs.cout * cs.k * cs.k * cs.cin;
   if (p.precision != DDN_PRECISION_FP32_SIMT && tc_conv_supported(cs.cin, cs.cout, cs.k, cs.stride, cs.pad, cs.dil, Hin, Win)) {
     return tc_conv_backward(in, w, dy, dx, addend, dw, N, Hin, Win, cs.cin, cs.cout, cs.k, cs.pad, cs.dil, p.precision,
                             c.ws + p.tc, p.tc_bytes, c.f(p.dwp), c.st);
@@ -280,12 +312,16 @@ static int conv_backward(const Ctx& c, const ConvSpec& cs, const float* in, cons
   DDN_TRY(conv_geom_init(&g, N, Hin, Win, cin_eff, Hout, Wout, cs.cout, cs.k, cs.k, cs.stride, 1, cs.pad, cs.dil));
   size_t wbytes = sizeof(float) * (size_t)cs.k * cs.k * cin_eff * cs.cout;
   DDN_TRY(launch_fill_zero(c.f(p.dwp), wbytes, c.st));
-  DDN_TRY(launch_conv_wgrad_f32(in, dy, c.f(p.dwp), g, c.st));
+  {
+    ProfScope ps(PROF_CONV_WGRAD_SIMT, fl, c.st);
+    DDN_TRY(launch_conv_wgrad_f32(in, dy, c.f(p.dwp), g, c.st));
+  }
   DDN_TRY(launch_unpack_wgrad(c.f(p.dwp), dw, cs.cout, cs.cin, cin_eff, cs.k, cs.k, c.st));
   if (dx) {
     ConvGeom gd;
     DDN_TRY(conv_geom_init(&gd, N, Hout, Wout, cs.cout, Hin, Win, cs.cin, cs.k, cs.k, 1, cs.stride, cs.dil * (cs.k - 1) - cs.pad, cs.dil));
     DDN_TRY(launch_pack_weights(w, c.f(p.wpack2), cs.cout, cs.cin, cs.cin, cs.k, cs.k, 1, c.st));
+    ProfScope ps(PROF_CONV_DGRAD_SIMT, fl, c.st);
     DDN_TRY(launch_conv_gather_f32(dy, c.f(p.wpack2), addend, dx, gd, c.st));
   }
   return 0;
@@ -350,6 +386,34 @@ using namespace ddn;
 extern "C" int ddn_abi_version(void) { return DDN_ABI_VERSION; }
 extern "C" const char* ddn_last_error(void) { return g_err; }
 extern "C" int64_t ddn_kernel_launch_count(void) { return g_launches.load(); }
+
+extern "C" int ddn_profile_enable(int on) { g_prof_on.store(on ? 1 : 0); return 0; }
+extern "C" int ddn_profile_reset(void) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_used = 0;
+  return 0;
+}
+extern "C" int ddn_profile_read(ddn_profile_entry* out, int cap) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  double ms[PROF_NUM_CLASSES] = {0}, work[PROF_NUM_CLASSES] = {0};
+  int64_t n[PROF_NUM_CLASSES] = {0};
+  for (size_t i = 0; i < g_prof_used; ++i) {
+    float t = 0.f;
+    if (cudaEventSynchronize(g_prof[i].b) != cudaSuccess || cudaEventElapsedTime(&t, g_prof[i].a, g_prof[i].b) != cudaSuccess) continue;
+    ms[g_prof[i].cls] += t; work[g_prof[i].cls] += g_prof[i].work; n[g_prof[i].cls]++;
+  }
+  int k = 0;
+  for (int c = 0; c < PROF_NUM_CLASSES; ++c) {
+    if (!n[c]) continue;
+    if (out && k < cap) {
+      memset(&out[k], 0, sizeof(out[k]));
+      snprintf(out[k].name, sizeof(out[k].name), "%s", kProfNames[c]);
+      out[k].launches = n[c]; out[k].ms = ms[c]; out[k].work = work[c];
+    }
+    ++k;
+  }
+  return k;
+}
 
 extern "C" int ddn_resnet34_8s_param_table(int D, ddn_tensor_entry* out, int cap) {
   if (D < 1 || D > 32) return DDN_EINVAL;

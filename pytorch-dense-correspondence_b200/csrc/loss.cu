@@ -317,6 +317,9 @@ extern "C" int ddn_contrastive_terms_forward(const float* pred_a, const float* p
   if (T.total_blocks == 0) return 0;
   dim3 grid(T.total_blocks, B);
   auto cnt = reinterpret_cast<unsigned long long*>(counts);
+  double pairs = 0;
+  for (int i = 0; i < n_terms; ++i) pairs += (double)terms_host[i].n * B;
+  ProfScope ps(PROF_LOSS_FWD, pairs * (16.0 + 8.0 * D), st);
 #define FWD(DT) DDN_LAUNCH(loss_terms_fwd_kernel<DT>, grid, LOSS_THREADS, 0, st, pred_a, pred_b, stride_b, stride_p, \
                            stride_c, P, D, image_width, T, sums, cnt)
   switch (D) {
@@ -342,6 +345,9 @@ extern "C" int ddn_contrastive_terms_backward(const float* pred_a, const float* 
   if (T.total_blocks == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(T.total_blocks, B);
+  double pairs = 0;
+  for (int i = 0; i < n_terms; ++i) pairs += (double)terms_host[i].n * B;
+  ProfScope ps(PROF_LOSS_BWD, pairs * (16.0 + 24.0 * D), st);
 #define BWD(DT) DDN_LAUNCH(loss_terms_bwd_kernel<DT>, grid, LOSS_THREADS, 0, st, pred_a, pred_b, stride_b, stride_p, \
                            stride_c, P, D, image_width, T, coef, upstream, dpred_a, dpred_b)
   switch (D) {

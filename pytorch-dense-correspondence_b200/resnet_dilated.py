@@ -50,7 +50,7 @@ class _Backbone(torch.autograd.Function):
         D = owner.num_classes
         flat, bufs = owner._ensure_flat(x.device)
         training = 1 if owner.training else 0
-        keep = training and torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        keep = bool(training) and any(ctx.needs_input_grad)   # grad mode is off inside Function.forward; this is the signal
         prec = owner.precision
         ws_bytes = N.lib.ddn_resnet34_8s_workspace_bytes(B, H, W, D, training, prec)
         if ws_bytes == 0:

@@ -1,0 +1,233 @@
+"""GPU: Resnet34_8s forward / backward and the whole training step through the reference-facing Python API
+against the CPU oracle (and the golden vectors written from the real reference).
+
+Gates (BASELINE.json north_star): descriptors within 1e-3 relative fp32, scalar loss within 1e-4."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import pdc_b200
+from pdc_b200 import loss_composer, synthetic, _native as N
+from oracle import loss_oracle as LO
+from oracle.resnet34_8s_oracle import seeded_oracle, process_network_output
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+PRECISIONS = ["fp32"] + (["bf16x3"] if os.environ.get("DDN_TEST_TC", "1") == "1" else [])
+
+
+def rel(a, b):
+    a = a.double().cpu(); b = b.double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def relmax(a, b):
+    a = a.double().cpu(); b = b.double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def make_net(D, precision="fp32", oracle=None):
+    oracle = oracle or seeded_oracle(D=D, seed=0)
+    prec = {"fp32": N.PRECISION_FP32_SIMT, "bf16x3": N.PRECISION_BF16X3, "bf16": N.PRECISION_BF16}[precision]
+    net = pdc_b200.Resnet34_8s(num_classes=D, precision=prec)
+    net.load_state_dict(oracle.state_dict())
+    return net.cuda(), oracle
+
+
+def cuda_oracle_grads(D, x, cot):
+    """PyTorch's own CUDA fp32 (cuDNN, TF32 off) run of the oracle: its distance from the CPU oracle is the noise
+    floor of this network's gradients (ReLU / max-pool decisions flip on 1-ulp differences and train-mode BN amplifies
+    them), so gradient gates are expressed relative to it instead of as an absolute number."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    o = seeded_oracle(D).train().cuda()
+    y = o(x.to(DEV))
+    (y * cot.to(DEV)).sum().backward()
+    return {k: p.grad.detach().cpu() for k, p in o.named_parameters()}
+
+
+def check_param_grads(net, ref_grads, floor_grads, factor=3.0, strict=2e-3, label=""):
+    """ref_grads: CPU-oracle (or golden) gradients; floor_grads: the cuDNN fp32 run of the same step."""
+    worst = 0.0
+    num = den = 0.0
+    scale = max(float(r.double().norm()) for r in ref_grads.values())
+    for k, p in net.named_parameters():
+        if k not in ref_grads:
+            continue
+        r = ref_grads[k]
+        if float(r.double().norm()) < 1e-5 * scale:
+            # e.g. fc.bias under the contrastive loss: d/dA and d/dB cancel exactly in exact arithmetic, what is left is
+            # rounding noise in every implementation -> only require it to stay negligible
+            assert float(p.grad.double().norm()) < 1e-4 * scale, k
+            continue
+        e = rel(p.grad, r)
+        floor = rel(floor_grads[k], r) if floor_grads is not None and k in floor_grads else 0.0
+        assert e <= max(strict, factor * floor), "%s %s: rel err %.3e vs noise floor %.3e" % (label, k, e, floor)
+        worst = max(worst, e)
+        num += float((p.grad.double().cpu() - r.double()).norm() ** 2); den += float(r.double().norm() ** 2)
+    return worst, (num / den) ** 0.5
+
+
+WELL_CONDITIONED = ("resnet34_8s.fc.weight", "resnet34_8s.fc.bias")
+
+
+def tc_or_skip(precision):
+    if precision != "fp32" and N.lib.ddn_resnet34_8s_workspace_bytes(1, 64, 64, 3, 1, N.PRECISION_BF16X3) == 0:
+        pytest.skip("tcgen05 path not in this build")
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("name,D,B,H,W", [("backbone_small_d3", 3, 2, 64, 96), ("backbone_small_d16", 16, 1, 48, 64)])
+def test_backbone_small_vs_golden(golden_dir, precision, name, D, B, H, W):
+    tc_or_skip(precision)
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    net, _ = make_net(D, precision)
+    gen = torch.Generator().manual_seed(int(g["x_seed"]))
+    x = torch.randn(B, 3, H, W, generator=gen)
+    cot = torch.randn(B, D, H, W, generator=gen)
+    net.train()
+    y = net(x.to(DEV))
+    assert y.shape == (B, D, H, W) and y.is_contiguous()
+    tol = 1e-3
+    assert rel(y, torch.tensor(g["y_train"])) < tol and relmax(y, torch.tensor(g["y_train"])) < tol
+    sd = net.state_dict()
+    for k in g.files:
+        if k.startswith("rs:"):
+            assert rel(sd[k[3:]], torch.tensor(g[k])) < 1e-3, k
+    assert int(sd["resnet34_8s.bn1.num_batches_tracked"]) == 1
+    (y * cot.to(DEV)).sum().backward()
+    params = dict(net.named_parameters())
+    golden_grads = {k[5:]: torch.tensor(g[k]) for k in g.files if k.startswith("grad:")}
+    floor = cuda_oracle_grads(D, x, cot)
+    check_param_grads(net, golden_grads, floor, label=name)
+    for k in WELL_CONDITIONED:          # the last layer sees no ReLU/BN chaos: tight absolute gate
+        assert rel(params[k].grad, golden_grads[k]) < (1e-4 if precision == "fp32" else 1e-3), k
+    norms = np.array([float(p.grad.double().norm()) for _, p in net.named_parameters()])
+    np.testing.assert_allclose(norms, g["gradnorm:all"], rtol=3e-2)
+    net.eval()
+    with torch.no_grad():
+        ye = net(x.to(DEV))
+    assert rel(ye, torch.tensor(g["y_eval"])) < tol
+    assert int(net.state_dict()["resnet34_8s.bn1.num_batches_tracked"]) == 1     # eval does not count
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_backbone_full_size_vs_golden_and_oracle(golden_dir, precision):
+    """640x480, D=3: the golden sub-sampled descriptors (from the real reference) and the full oracle output."""
+    tc_or_skip(precision)
+    g = np.load(os.path.join(golden_dir, "backbone_full_d3.npz"))
+    net, oracle = make_net(3, precision)
+    gen = torch.Generator().manual_seed(int(g["x_seed"]))
+    x = torch.randn(1, 3, 480, 640, generator=gen)
+    cot = torch.randn(1, 3, 480, 640, generator=gen)
+    net.train(); oracle.train()
+    y = net(x.to(DEV))
+    assert rel(y[:, :, ::16, ::16], torch.tensor(g["y_train"])) < 1e-3
+    y_or = oracle(x)
+    assert rel(y, y_or.detach()) < 1e-3 and relmax(y, y_or.detach()) < 1e-3
+    (y * cot.to(DEV)).sum().backward()
+    params = dict(net.named_parameters())
+    (y_or * cot).sum().backward()
+    oracle_grads = {k: p.grad for k, p in oracle.named_parameters()}
+    floor = cuda_oracle_grads(3, x, cot)
+    worst, agg = check_param_grads(net, oracle_grads, floor, label="full")
+    print("full-size gradients: worst per-tensor rel err %.2e, aggregate %.2e" % (worst, agg))
+    for k in g.files:                   # and the committed sub-set written from the real reference
+        if k.startswith("grad:"):
+            assert rel(oracle_grads[k[5:]], torch.tensor(g[k])) < 1e-4, k
+    for k in WELL_CONDITIONED:
+        assert rel(params[k].grad, oracle_grads[k]) < (1e-4 if precision == "fp32" else 1e-3), k
+    norms = np.array([float(p.grad.double().norm()) for _, p in net.named_parameters()])
+    np.testing.assert_allclose(norms, g["gradnorm:all"], rtol=3e-2)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_train_step_small_vs_golden(golden_dir, precision):
+    """fwd(A), fwd(B), loss_composer.get_loss, backward -- exactly the calls of training.py:329-345 -- on a
+    batch of 2 pairs; golden written from the real reference backbone + restated loss."""
+    tc_or_skip(precision)
+    g = np.load(os.path.join(golden_dir, "train_step_small_d3.npz"))
+    D, B, H, W = 3, 2, 64, 96
+    cfg = {"descriptor_dimension": D, "image_width": W, "image_height": H}
+    dcn = pdc_b200.DenseCorrespondenceNetwork.from_config(cfg, load_stored_params=False)
+    assert dcn.training and next(dcn.parameters()).is_cuda
+    dcn.fcn.precision = {"fp32": 0, "bf16x3": 1}[precision]
+    dcn.fcn.load_state_dict(seeded_oracle(D).state_dict())
+    data = synthetic.make_pair_batch(B, H, W, 40, 120, 120, 0, seed=int(g["seed"]))
+    d = {k: (v.to(DEV) if v is not None else None) for k, v in data.items()}
+    pcl = pdc_b200.PixelwiseContrastiveLoss(image_shape=dcn.image_shape, config=dict(LO.DEFAULT_LOSS_CONFIG))
+    opt = torch.optim.Adam(dcn.parameters(), lr=1e-4, weight_decay=1e-4)
+    opt.zero_grad()
+    pa = dcn.process_network_output(dcn.forward(d["img_a"]), B)
+    pb = dcn.process_network_output(dcn.forward(d["img_b"]), B)
+    blind = loss_composer.empty_tensor().to(DEV)
+    five = loss_composer.get_loss(pcl, torch.tensor([0, 0]), pa, pb, d["matches_a"], d["matches_b"], d["masked_a"],
+                                  d["masked_b"], d["background_a"], d["background_b"], blind, blind)
+    got = np.array([float(t) for t in five])
+    np.testing.assert_allclose(got, g["five"], rtol=1e-4, atol=1e-7)
+    five[0].backward()
+    params = dict(dcn.fcn.named_parameters())
+    # noise floor for this step: the oracle on CUDA (cuDNN fp32) with the restated loss
+    torch.backends.cudnn.allow_tf32 = False
+    o = seeded_oracle(D).train().cuda()
+    pcl_o = LO.TorchPixelwiseContrastiveLoss([H, W], dict(LO.DEFAULT_LOSS_CONFIG))
+    ya, yb = o(d["img_a"]), o(d["img_b"])
+    five_o = LO.batched_within_scene_loss(pcl_o, process_network_output(ya, B, D, H, W),
+                                          process_network_output(yb, B, D, H, W), d)
+    five_o[0].backward()
+    floor = {k: p.grad.detach().cpu() for k, p in o.named_parameters()}
+    golden_grads = {k[5:]: torch.tensor(g[k]) for k in g.files if k.startswith("grad:")}
+    check_param_grads(dcn.fcn, golden_grads, floor, strict=5e-3, label="train_step")
+    assert rel(params["resnet34_8s.fc.weight"].grad, golden_grads["resnet34_8s.fc.weight"]) < (2e-4 if precision == "fp32" else 2e-3)
+    assert rel(dcn.state_dict()["_fcn.resnet34_8s.bn1.running_mean"], torch.tensor(g["rs:resnet34_8s.bn1.running_mean"])) < 1e-3
+    before = dcn.fcn.flat_parameters.clone()
+    opt.step()                                      # Adam updates the views == the flat array the kernels read
+    assert float((dcn.fcn.flat_parameters - before).abs().max()) > 0
+    assert int(dcn.state_dict()["_fcn.resnet34_8s.bn1.num_batches_tracked"]) == 2
+
+
+def test_single_image_inference_and_state_dict_roundtrip(tmp_path):
+    D = 3
+    net, oracle = make_net(D)
+    dcn = pdc_b200.DenseCorrespondenceNetwork(net, D, image_width=96, image_height=64)
+    dcn.eval(); oracle.eval()
+    x = torch.randn(3, 64, 96, generator=torch.Generator().manual_seed(4))
+    res = dcn.forward_single_image_tensor(x)
+    assert res.shape == (64, 96, D)
+    with torch.no_grad():
+        ref = oracle(x.unsqueeze(0))[0].permute(1, 2, 0)
+    assert rel(res, ref) < 1e-3
+    uv, diff, nd = dcn.find_best_match((10, 20), res.detach().cpu().numpy(), res.detach().cpu().numpy())
+    assert uv == (10, 20) and diff == 0.0 and nd.shape == (64, 96)
+    f = tmp_path / "000001.pth"
+    torch.save(dcn.state_dict(), f)
+    assert all(k.startswith("_fcn.resnet34_8s.") for k in dcn.state_dict())
+    cfg = {"descriptor_dimension": D, "image_width": 96, "image_height": 64}
+    import yaml
+    (tmp_path / "training.yaml").write_text(yaml.safe_dump({"dense_correspondence_network": cfg}))
+    dcn2 = pdc_b200.DenseCorrespondenceNetwork.from_model_folder(str(tmp_path))
+    dcn2.eval()
+    assert torch.equal(dcn2.forward_single_image_tensor(x), res)
+    # a reference-style checkpoint (keys without the _fcn. prefix) loads through the fallback of net.py:429-433
+    torch.save(oracle.state_dict(), tmp_path / "000002.pth")
+    dcn3 = pdc_b200.DenseCorrespondenceNetwork.from_model_folder(str(tmp_path), iteration=2)
+    dcn3.eval()
+    assert torch.equal(dcn3.forward_single_image_tensor(x), res)
+
+
+def test_contract_errors_on_gpu():
+    net, _ = make_net(3)
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 3, 60, 80, device=DEV))                  # not multiples of 8
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 3, 64, 64, device=DEV, dtype=torch.float16))
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 4, 64, 64, device=DEV))
+    with pytest.raises(NotImplementedError):
+        net(torch.zeros(1, 3, 64, 64, device=DEV), feature_alignment=True)
+    net.eval()
+    y = net(torch.zeros(1, 3, 64, 64, device=DEV).requires_grad_())
+    with pytest.raises(RuntimeError):
+        y.sum().backward()                                           # eval-mode forward keeps nothing

@@ -1,0 +1,240 @@
+"""GPU: every single-operator C-ABI entry point against a plain PyTorch fp32 CPU reference of the same op
+(tolerances written per test), and the loss kernels against the oracle / golden vectors."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import pdc_b200
+from pdc_b200 import ops, loss_composer, _native as N
+from pdc_b200.contrastive_ops import Term, contrastive_terms
+from oracle import loss_oracle as LO
+from oracle.resnet34_8s_oracle import process_network_output
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rel(a, b):
+    a = a.double().cpu(); b = b.double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+CONV_CASES = [
+    # N, H, W, Cin, Cout, k, stride, pad, dil
+    (2, 30, 40, 64, 64, 3, 1, 1, 1),      # layer1
+    (1, 30, 40, 64, 128, 3, 2, 1, 1),     # layer2.0.conv1
+    (1, 30, 40, 64, 128, 1, 2, 0, 1),     # layer2.0.downsample
+    (1, 15, 20, 128, 256, 3, 1, 2, 2),    # layer3.0.conv1 (dilation 2)
+    (2, 15, 20, 256, 256, 3, 1, 2, 2),
+    (1, 15, 20, 256, 512, 3, 1, 4, 4),    # layer4.0.conv1 (dilation 4)
+    (1, 15, 20, 256, 512, 1, 1, 0, 1),    # layer4.0.downsample
+    (1, 13, 9, 512, 512, 3, 1, 4, 4),     # odd sizes, M not a tile multiple
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv2d_forward_backward_fp32(case):
+    n, h, w, cin, cout, k, s, p, d = case
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) * (2.0 / (k * k * cin)) ** 0.5
+    xr = x.clone().requires_grad_(); wr = wt.clone().requires_grad_()
+    y_ref = F.conv2d(xr, wr, None, s, p, d)
+    dy = torch.randn(y_ref.shape, generator=g)
+    y_ref.backward(dy)
+    y = ops.conv2d_forward(nhwc(x).to(DEV), wt.to(DEV), s, p, d)
+    assert rel(y, nhwc(y_ref.detach())) < 2e-6          # fp32 FFMA vs fp32 CPU: summation order only
+    dx, dw = ops.conv2d_backward(nhwc(x).to(DEV), wt.to(DEV), nhwc(dy).to(DEV), s, p, d)
+    assert rel(dx, nhwc(xr.grad)) < 2e-6
+    assert rel(dw, wr.grad) < 5e-6                       # split-K fp32 atomics
+
+
+@pytest.mark.parametrize("C,relu,residual", [(64, True, False), (128, True, True), (256, False, False), (512, True, True)])
+def test_batchnorm_forward_backward(C, relu, residual):
+    g = torch.Generator().manual_seed(C)
+    M = 2 * 15 * 20
+    x = torch.randn(M, C, generator=g) * 2 + 0.5
+    gamma = torch.rand(C, generator=g) + 0.5; beta = torch.randn(C, generator=g)
+    res = torch.randn(M, C, generator=g) if residual else None
+    rm = torch.zeros(C); rv = torch.ones(C)
+    xr = x.clone().requires_grad_(); gr = gamma.clone().requires_grad_(); br = beta.clone().requires_grad_()
+    rr = res.clone().requires_grad_() if residual else None
+    y_ref = F.batch_norm(xr, rm, rv, gr, br, True, 0.1, 1e-5)
+    if residual:
+        y_ref = y_ref + rr
+    if relu:
+        y_ref = F.relu(y_ref)
+    dy = torch.randn(M, C, generator=g)
+    y_ref.backward(dy)
+    rmg = torch.zeros(C, device=DEV); rvg = torch.ones(C, device=DEV)
+    y, mean, invstd = ops.batchnorm_forward(x.to(DEV), gamma.to(DEV), beta.to(DEV), res.to(DEV) if residual else None,
+                                            relu=relu, training=True, running_mean=rmg, running_var=rvg)
+    assert rel(y, y_ref.detach()) < 2e-6
+    assert rel(rmg, rm) < 1e-6 and rel(rvg, rv) < 1e-6     # momentum 0.1, unbiased variance
+    dx, dgamma, dbeta, dres = ops.batchnorm_backward(dy.to(DEV), x.to(DEV), y, gamma.to(DEV), mean, invstd, relu=relu,
+                                                     need_residual_grad=residual)
+    assert rel(dx, xr.grad) < 1e-5
+    assert rel(dgamma, gr.grad) < 1e-5 and rel(dbeta, br.grad) < 1e-5
+    if residual:
+        assert rel(dres, rr.grad) < 1e-6
+    # eval mode uses the running statistics
+    ye, _, _ = ops.batchnorm_forward(x.to(DEV), gamma.to(DEV), beta.to(DEV), None, relu=False, training=False,
+                                     running_mean=rmg, running_var=rvg)
+    assert rel(ye, F.batch_norm(x, rm, rv, gamma, beta, False, 0.1, 1e-5)) < 2e-6
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 8, 12, 64, 96), (1, 16, 60, 80, 480, 640), (1, 3, 6, 8, 48, 64)])
+def test_upsample_bilinear(shape):
+    n, c, h, w, H, W = shape
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(n, c, h, w, generator=g, requires_grad=True)
+    y_ref = F.interpolate(x, size=(H, W), mode="bilinear", align_corners=True)
+    dy = torch.randn(y_ref.shape, generator=g)
+    y_ref.backward(dy)
+    y = ops.upsample_bilinear_forward(x.detach().to(DEV), H, W)
+    assert float((y.cpu() - y_ref.detach()).abs().max()) < 2e-5
+    dx = ops.upsample_bilinear_backward(dy.to(DEV), h, w)
+    assert rel(dx, x.grad) < 1e-5
+
+
+def _golden(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"))
+
+
+@pytest.mark.parametrize("name", ["loss_default_d3", "loss_pixelw_blind_d8", "loss_noscale_d16"])
+def test_fused_within_scene_loss_matches_golden(golden_dir, name):
+    g = _golden(golden_dir, name)
+    cfg = dict(LO.DEFAULT_LOSS_CONFIG)
+    for k, v in zip(g["cfg_keys"], g["cfg_vals"]):
+        k = str(k)
+        cfg[k] = bool(v) if isinstance(LO.DEFAULT_LOSS_CONFIG[k], bool) else float(v)
+    A = torch.tensor(g["A"], device=DEV).requires_grad_(); B = torch.tensor(g["B"], device=DEV).requires_grad_()
+    _, D, H, W = A.shape
+    pcl = pdc_b200.PixelwiseContrastiveLoss([H, W], cfg)
+    pa = A.view(1, D, H * W).permute(0, 2, 1); pb = B.view(1, D, H * W).permute(0, 2, 1)
+    idx = {k: torch.tensor(g[k], device=DEV) for k in ("matches_a", "matches_b", "masked_a", "masked_b",
+                                                       "background_a", "background_b", "blind_a", "blind_b")}
+    five = loss_composer.get_loss(pcl, torch.tensor([0]), pa, pb, idx["matches_a"], idx["matches_b"], idx["masked_a"],
+                                  idx["masked_b"], idx["background_a"], idx["background_b"], idx["blind_a"], idx["blind_b"])
+    got = np.array([float(t) for t in five])
+    np.testing.assert_allclose(got, g["five"], rtol=2e-6, atol=1e-7)        # north_star gate: 1e-4 on the scalar loss
+    five[0].backward()
+    assert rel(A.grad, torch.tensor(g["dA"])) < 1e-5 and rel(B.grad, torch.tensor(g["dB"])) < 1e-5
+    assert pcl.debug is False
+    pcl.debug = True
+    loss_composer.get_loss(pcl, torch.tensor([0]), pa, pb, idx["matches_a"], idx["matches_b"], idx["masked_a"],
+                           idx["masked_b"], idx["background_a"], idx["background_b"], idx["blind_a"], idx["blind_b"])
+    counts = pcl.debug_data["num_hard_negatives_device"][0].tolist()
+    assert counts[1] == int(g["counts"][0]) and counts[2] == int(g["counts"][1])     # hard negatives: exact
+    if not (len(g["blind_a"]) == 1 and g["blind_a"][0] == -1):
+        assert counts[3] == int(g["counts"][2])
+
+
+def test_loss_methods_match_oracle_and_edge_cases():
+    H, W, D = 24, 32, 5
+    gen = torch.Generator().manual_seed(3)
+    A = (0.3 * torch.randn(1, D, H, W, generator=gen)); B = (0.3 * torch.randn(1, D, H, W, generator=gen))
+    P = H * W
+    ma = torch.randint(0, P, (37,), generator=gen); mb = torch.randint(0, P, (37,), generator=gen)
+    na = ma.repeat_interleave(3); nb = torch.randint(0, P, (111,), generator=gen)
+    cfg = dict(LO.DEFAULT_LOSS_CONFIG); cfg["M_descriptor"] = 0.6
+    ref = LO.TorchPixelwiseContrastiveLoss([H, W], cfg)
+    ours = pdc_b200.PixelwiseContrastiveLoss([H, W], cfg)
+    Ar = A.clone().requires_grad_(); Br = B.clone().requires_grad_()
+    Ag = A.to(DEV).requires_grad_(); Bg = B.to(DEV).requires_grad_()
+    par, pbr = process_network_output(Ar, 1, D, H, W), process_network_output(Br, 1, D, H, W)
+    pag, pbg = process_network_output(Ag, 1, D, H, W), process_network_output(Bg, 1, D, H, W)
+    c = lambda t: t.to(DEV)
+    # match_loss
+    r = ref.match_loss(par, pbr, ma, mb)[0]; o = ours.match_loss(pag, pbg, c(ma), c(mb))[0]
+    assert abs(float(r) - float(o)) < 1e-6 * abs(float(r))
+    # descriptor-only, inverted, pixel-weighted
+    for fn, args_r, args_o, kw in [
+        ("non_match_loss_descriptor_only", (par, pbr, na, nb), (pag, pbg, c(na), c(nb)), dict(M_descriptor=0.6)),
+        ("non_match_loss_descriptor_only", (par, pbr, na, nb), (pag, pbg, c(na), c(nb)), dict(M_descriptor=0.3, invert=True)),
+        ("non_match_loss_with_l2_pixel_norm", (par, pbr, mb, na, nb), (pag, pbg, c(mb), c(na), c(nb)), dict(M_descriptor=0.6, M_pixel=9)),
+    ]:
+        rs, rh = getattr(ref, fn)(*args_r, **kw); os_, oh = getattr(ours, fn)(*args_o, **kw)
+        assert rh == oh, fn
+        assert abs(float(rs) - float(os_)) < 2e-6 * max(1.0, abs(float(rs))), fn
+    # combined + gradients through the generic autograd path
+    rm, rn, rh = ref.get_loss_matched_and_non_matched_with_l2(par, pbr, ma, mb, na, nb, M_descriptor=0.6)
+    om, on, oh = ours.get_loss_matched_and_non_matched_with_l2(pag, pbg, c(ma), c(mb), c(na), c(nb), M_descriptor=0.6)
+    assert rh == oh
+    (rm + 0.5 * rn).backward(); (om + 0.5 * on).backward()
+    assert rel(Ag.grad, Ar.grad) < 1e-5 and rel(Bg.grad, Br.grad) < 1e-5
+    # vector-returning method + legacy loss keep the reference's values
+    rv = ref.non_match_descriptor_loss(par, pbr, na, nb, M=0.6); ov = ours.non_match_descriptor_loss(pag, pbg, c(na), c(nb), M=0.6)
+    assert rv[1] == ov[1] and rel(ov[0], rv[0]) < 1e-6
+    rl = ref.get_loss_original(par, pbr, ma, mb, na, nb); ol = ours.get_loss_original(pag, pbg, c(ma), c(mb), c(na), c(nb))
+    assert abs(float(rl[0]) - float(ol[0])) < 1e-5
+    # single index pair, identical descriptors (d = 0 -> counted hard, zero gradient), contiguous [1,P,D] input
+    Z = torch.zeros(1, P, D, device=DEV, requires_grad=True)
+    s, h = ours.non_match_loss_descriptor_only(Z, Z.detach().clone(), c(torch.tensor([5])), c(torch.tensor([9])), M_descriptor=0.5)
+    assert h == 1 and abs(float(s) - 0.25) < 1e-7
+    s.backward()
+    assert float(Z.grad.abs().sum()) == 0.0
+    # different-object composition and the two pair types the reference cannot run
+    xa = torch.randint(0, P, (50,), generator=gen); xb = torch.randint(0, P, (50,), generator=gen)
+    rfive = LO.get_loss(ref, torch.tensor([2]), par, pbr, ma, mb, na, nb, na, nb, xa, xb)
+    ofive = loss_composer.get_loss(ours, torch.tensor([2]), pag, pbg, c(ma), c(mb), c(na), c(nb), c(na), c(nb), c(xa), c(xb))
+    assert abs(float(rfive[0]) - float(ofive[0])) < 1e-6 and abs(float(rfive[4]) - float(ofive[4])) < 1e-6
+    with pytest.raises((NameError, UnboundLocalError)):
+        loss_composer.get_loss(ours, torch.tensor([1]), pag, pbg, c(ma), c(mb), c(na), c(nb), c(na), c(nb), c(xa), c(xb))
+    with pytest.raises(ValueError):
+        loss_composer.get_loss(ours, torch.tensor([7]), pag, pbg, c(ma), c(mb), c(na), c(nb), c(na), c(nb), c(xa), c(xb))
+
+
+@pytest.mark.parametrize("D,n_nm", [(3, 150_000), (16, 5_000)])
+def test_loss_large_properties(D, n_nm):
+    """Full-size (640x480) size-independent properties: permutation invariance of the sums, linearity of the
+    backward in the upstream gradient, and duplicate-heavy A-side indices scatter exactly like index_add_."""
+    H, W, B = 480, 640, 2
+    P = H * W
+    gen = torch.Generator().manual_seed(9)
+    A = (0.2 * torch.randn(B, D, H, W, generator=gen)).to(DEV); Bt = (0.2 * torch.randn(B, D, H, W, generator=gen)).to(DEV)
+    pa = A.view(B, D, P).permute(0, 2, 1); pb = Bt.view(B, D, P).permute(0, 2, 1)
+    ma = torch.randint(0, P, (B, 1000), generator=gen).to(DEV); mb = torch.randint(0, P, (B, 1000), generator=gen).to(DEV)
+    na = ma.repeat_interleave(n_nm // 1000, dim=1); nb = torch.randint(0, P, (B, n_nm), generator=gen).to(DEV)
+    terms = lambda a, b: [Term(ma, mb, N.TERM_MATCH), Term(a, b, N.TERM_HINGE, 0.5)]
+    s1, c1 = contrastive_terms(pa, pb, W, terms(na, nb))
+    perm = torch.randperm(n_nm, generator=gen).to(DEV)
+    s2, c2 = contrastive_terms(pa, pb, W, terms(na[:, perm], nb[:, perm]))
+    assert torch.equal(c1, c2)
+    assert float(((s1 - s2).abs() / s1.abs().clamp(min=1e-12)).max()) < 1e-9
+    # against a torch (CUDA, fp32) composition of the same math
+    ga = torch.gather(pa, 1, na.unsqueeze(-1).expand(-1, -1, D)); gb = torch.gather(pb, 1, nb.unsqueeze(-1).expand(-1, -1, D))
+    dist = (ga - gb).norm(2, 2)
+    hinge = torch.clamp(0.5 - dist, min=0).pow(2)
+    assert float(((hinge.double().sum(1) - s1[:, 1]).abs() / s1[:, 1]).max()) < 1e-5
+    assert torch.equal((hinge != 0).sum(1), c1[:, 1])
+    # backward: linear in upstream, equals autograd of the torch composition
+    Ar = A.clone().requires_grad_(); Br = Bt.clone().requires_grad_()
+    par = Ar.view(B, D, P).permute(0, 2, 1); pbr = Br.view(B, D, P).permute(0, 2, 1)
+    ga = torch.gather(par, 1, na.unsqueeze(-1).expand(-1, -1, D)); gb = torch.gather(pbr, 1, nb.unsqueeze(-1).expand(-1, -1, D))
+    torch.clamp(0.5 - (ga - gb).norm(2, 2), min=0).pow(2).sum().backward()
+    Ag = A.clone().requires_grad_(); Bg = Bt.clone().requires_grad_()
+    s, _ = contrastive_terms(Ag.view(B, D, P).permute(0, 2, 1), Bg.view(B, D, P).permute(0, 2, 1), W, terms(na, nb))
+    (3.0 * s[:, 1].sum()).backward()
+    assert rel(Ag.grad, 3.0 * Ar.grad) < 1e-5 and rel(Bg.grad, 3.0 * Br.grad) < 1e-5
+
+
+def test_host_buffer_entry_point(golden_dir):
+    import ctypes
+    g = _golden(golden_dir, "loss_default_d3")
+    A = np.ascontiguousarray(g["A"]); B = np.ascontiguousarray(g["B"])
+    _, D, H, W = A.shape
+    five = np.zeros(5, dtype=np.float32)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    idx = [np.ascontiguousarray(g[k]) for k in ("matches_a", "matches_b", "masked_a", "masked_b", "background_a", "background_b")]
+    rc = N.lib.ddn_within_scene_loss_host(p(A), p(B), 1, H, W, D, p(idx[0]), p(idx[1]), len(idx[0]), p(idx[2]), p(idx[3]),
+                                          len(idx[2]), p(idx[4]), p(idx[5]), len(idx[4]), 0.5, 0.5, 1.0, 1.0, 1, p(five))
+    N.check(rc)
+    np.testing.assert_allclose(five[:4], g["five"][:4], rtol=2e-6, atol=1e-7)
