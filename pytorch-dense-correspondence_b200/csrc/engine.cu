@@ -223,7 +223,7 @@ static int make_plan(Plan* p, int B, int H, int W, int D, int training, int prec
   p->partial = f32(max_partial * 2);
   p->scratch_elems = (size_t)max_act;
   for (int i = 0; i < 4; ++i) p->scratch[i] = f32((int64_t)max_act);
-  p->tc_bytes = precision == DDN_PRECISION_FP32_SIMT ? 0 : tc_workspace_bytes(B, p->Hp, p->Wp);
+  p->tc_bytes = precision == DDN_PRECISION_FP32_SIMT ? 0 : tc_workspace_bytes((size_t)max_act);
   p->tc = alloc(p->tc_bytes);
   p->total = cur;
   return 0;
@@ -241,7 +241,6 @@ static int conv_forward(const Ctx& c, const ConvSpec& cs, const float* in, float
   const float* w = c.params + cs.w_off;
   const double fl = 2.0 * N * Hout * Wout * (double)cs.cout * cs.k * cs.k * cs.cin;
   if (c.p->precision != DDN_PRECISION_FP32_SIMT && tc_conv_supported(cs.cin, cs.cout, cs.k, cs.stride, cs.pad, cs.dil, Hin, Win)) {
-    ProfScope ps(PROF_CONV_FWD_TC, fl, c.st);
     return tc_conv_forward(in, w, out, N, Hin, Win, cs.cin, cs.cout, cs.k, cs.pad, cs.dil, c.p->precision,
                            c.ws + c.p->tc, c.p->tc_bytes, c.st);
   }
@@ -468,7 +467,7 @@ static int conv_out(int in, int k, int stride, int pad, int dil) { return (in + 
 
 extern "C" size_t ddn_conv2d_workspace_bytes(int N, int H, int W, int Cin, int Cout, int k, int stride, int pad, int dil, int precision) {
   size_t wb = align_up(sizeof(float) * (size_t)k * k * Cin * Cout, 256);
-  size_t tc = precision == DDN_PRECISION_FP32_SIMT ? 0 : tc_workspace_bytes(N, H, W);
+  size_t tc = precision == DDN_PRECISION_FP32_SIMT ? 0 : tc_workspace_bytes((size_t)N * H * W * (Cin > Cout ? Cin : Cout));
   return 3 * wb + align_up(tc, 256) + 256;
 }
 

@@ -56,6 +56,38 @@ def test_conv2d_forward_backward_fp32(case):
     assert rel(dw, wr.grad) < 5e-6                       # split-K fp32 atomics
 
 
+TC_CASES = [c for c in CONV_CASES if c[6] == 1] + [
+    (1, 60, 80, 64, 64, 3, 1, 1, 1),       # exact tiles (W = 5 x 16), Cout = 64 path
+    (2, 60, 80, 512, 512, 3, 1, 4, 4),     # the dominant GEMM: 72 k-blocks, 4 N-tiles
+    (1, 8, 12, 512, 512, 3, 1, 4, 4),      # feature map smaller than one 8x16 tile
+    (1, 60, 80, 128, 256, 1, 1, 0, 1),     # 1x1 downsample (layer3.0)
+]
+
+
+@pytest.mark.parametrize("precision,tol", [("bf16x3", 2e-5), ("bf16", 8e-3)])
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv2d_tcgen05(case, precision, tol):
+    """tcgen05 implicit GEMM vs the fp32 CPU reference: bf16x3 split must be fp32-class (<= 2e-5 relative Frobenius
+    error, ~2^-16 per product), single-pass bf16 within bf16 rounding."""
+    prec = {"bf16x3": N.PRECISION_BF16X3, "bf16": N.PRECISION_BF16}[precision]
+    if N.lib.ddn_resnet34_8s_workspace_bytes(1, 64, 64, 3, 1, prec) == 0:
+        pytest.skip("tcgen05 path not in this build")
+    n, h, w, cin, cout, k, s, p, d = case
+    g = torch.Generator().manual_seed(hash(case) % 1000 + 1)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) * (2.0 / (k * k * cin)) ** 0.5
+    xr = x.clone().requires_grad_(); wr = wt.clone().requires_grad_()
+    y_ref = F.conv2d(xr, wr, None, s, p, d)
+    dy = torch.randn(y_ref.shape, generator=g)
+    y_ref.backward(dy)
+    y = ops.conv2d_forward(nhwc(x).to(DEV), wt.to(DEV), s, p, d, precision=prec)
+    torch.cuda.synchronize()
+    assert rel(y, nhwc(y_ref.detach())) < tol
+    dx, dw = ops.conv2d_backward(nhwc(x).to(DEV), wt.to(DEV), nhwc(dy).to(DEV), s, p, d, precision=prec)
+    assert rel(dx, nhwc(xr.grad)) < tol
+    assert rel(dw, wr.grad) < max(tol, 5e-6)
+
+
 @pytest.mark.parametrize("C,relu,residual", [(64, True, False), (128, True, True), (256, False, False), (512, True, True)])
 def test_batchnorm_forward_backward(C, relu, residual):
     g = torch.Generator().manual_seed(C)
