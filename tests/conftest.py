@@ -11,6 +11,9 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+    # the GPU boxes advertise 128 logical CPUs to a throttled container: 128 torch threads make the CPU oracle ~50x slower
+    import torch
+    torch.set_num_threads(max(1, min(16, os.cpu_count() or 1)))
 
 
 def pytest_collection_modifyitems(config, items):

@@ -48,8 +48,13 @@ def cuda_oracle_grads(D, x, cot):
     return {k: p.grad.detach().cpu() for k, p in o.named_parameters()}
 
 
-def check_param_grads(net, ref_grads, floor_grads, factor=3.0, strict=2e-3, label=""):
-    """ref_grads: CPU-oracle (or golden) gradients; floor_grads: the cuDNN fp32 run of the same step."""
+def check_param_grads(net, ref_grads, floor_grads, factor=3.0, strict=2e-3, label="", precision="fp32"):
+    """ref_grads: CPU-oracle (or golden) gradients; floor_grads: the cuDNN fp32 run of the same step.
+    bf16x3 carries ~2^-17 per operand instead of 2^-24: its forward error is 5e-5..8e-5 (gate 1e-3), which the
+    cancellation-heavy per-channel sums (BN beta/gamma gradients) amplify to a few 1e-3 even where fp32 runs agree to
+    1e-6, and the chaotic tensors land at up to ~3.5x the fp32 noise floor (measured)."""
+    if precision != "fp32":
+        factor, strict = max(factor, 5.0), max(strict, 1e-2)
     worst = 0.0
     num = den = 0.0
     scale = max(float(r.double().norm()) for r in ref_grads.values())
@@ -101,7 +106,7 @@ def test_backbone_small_vs_golden(golden_dir, precision, name, D, B, H, W):
     params = dict(net.named_parameters())
     golden_grads = {k[5:]: torch.tensor(g[k]) for k in g.files if k.startswith("grad:")}
     floor = cuda_oracle_grads(D, x, cot)
-    check_param_grads(net, golden_grads, floor, label=name)
+    check_param_grads(net, golden_grads, floor, label=name, precision=precision)
     for k in WELL_CONDITIONED:          # the last layer sees no ReLU/BN chaos: tight absolute gate
         assert rel(params[k].grad, golden_grads[k]) < (1e-4 if precision == "fp32" else 1e-3), k
     norms = np.array([float(p.grad.double().norm()) for _, p in net.named_parameters()])
@@ -132,7 +137,7 @@ def test_backbone_full_size_vs_golden_and_oracle(golden_dir, precision):
     (y_or * cot).sum().backward()
     oracle_grads = {k: p.grad for k, p in oracle.named_parameters()}
     floor = cuda_oracle_grads(3, x, cot)
-    worst, agg = check_param_grads(net, oracle_grads, floor, label="full")
+    worst, agg = check_param_grads(net, oracle_grads, floor, label="full", precision=precision)
     print("full-size gradients: worst per-tensor rel err %.2e, aggregate %.2e" % (worst, agg))
     for k in g.files:                   # and the committed sub-set written from the real reference
         if k.startswith("grad:"):
@@ -179,7 +184,7 @@ def test_train_step_small_vs_golden(golden_dir, precision):
     five_o[0].backward()
     floor = {k: p.grad.detach().cpu() for k, p in o.named_parameters()}
     golden_grads = {k[5:]: torch.tensor(g[k]) for k in g.files if k.startswith("grad:")}
-    check_param_grads(dcn.fcn, golden_grads, floor, strict=5e-3, label="train_step")
+    check_param_grads(dcn.fcn, golden_grads, floor, strict=5e-3, label="train_step", precision=precision)
     assert rel(params["resnet34_8s.fc.weight"].grad, golden_grads["resnet34_8s.fc.weight"]) < (2e-4 if precision == "fp32" else 2e-3)
     assert rel(dcn.state_dict()["_fcn.resnet34_8s.bn1.running_mean"], torch.tensor(g["rs:resnet34_8s.bn1.running_mean"])) < 1e-3
     before = dcn.fcn.flat_parameters.clone()
