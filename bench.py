@@ -262,6 +262,11 @@ def run_ours(args):
     N.lib.ddn_profile_enable(0)
     prof = N.profile_read()
 
+    if args.profile_run:
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step_under_profiler": ms_total / args.steps, "classes": prof}))
+        return
+
     # ---- timed region 2: end to end from pinned host memory, loss read back every step
     def e2e_step():
         d = {k: pinned[k].to(dev, non_blocking=True) for k in keys}
@@ -347,6 +352,8 @@ def main():
     ap.add_argument("--non-matches", type=int, default=1000)
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-run", action="store_true",
+                    help="short run for ncu: 1 warm-up + --steps timed steps, no e2e / cpu legs (numbers printed are NOT bench values)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -355,7 +362,9 @@ def main():
         if world == 1 and args.gpus > 1:
             sys.stderr.write("bench.py: --gpus %d needs a torchrun launch (WORLD_SIZE=%d); see the module docstring\n" % (args.gpus, world))
             sys.exit(2)
-    if args.warmup < 3:
+    if args.profile_run:
+        args.warmup, args.no_cpu_baseline = 1, True
+    elif args.warmup < 3:
         args.warmup = 3
     run_ours(args)
 

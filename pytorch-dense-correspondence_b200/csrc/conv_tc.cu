@@ -84,6 +84,19 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// MN-major, 128-byte swizzle descriptor: LBO = byte distance between 64-element atoms along M/N, SBO = between 8-row K groups
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_bf16_mn(int M, int N) {   // both operands MN-major
+  return make_idesc_bf16(M, N) | (1u << 15) | (1u << 16);
+}
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
@@ -249,6 +262,196 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ weight gradient
+// dW[co][tap][ci] = sum_pixels dY[pixel][co] * X[pixel + offset(tap)][ci]  as a tcgen05 GEMM with the PIXELS as the K
+// dimension.  Both operands are the same NHWC bf16 planes the forward reads, consumed as MN-MAJOR UMMA operands
+// (channels contiguous, pixels = K rows), so no transposed copy exists anywhere:
+//   A = dY patch: 64 pixels (4x16) x 128 output channels = two TMA boxes {64 c, 16 w, 4 h, 1 n}, 8 KB each
+//   B = X  patch: 64 shifted pixels x BN input channels   = BN/64 boxes at (w0+(s-1)dil, h0+(r-1)dil); OOB zero fill
+//                                                            is the padding, the shift only touches the W/H coordinates
+// In shared memory a box is 64 rows (pixels) of 128 swizzled bytes (64 channels): the canonical MN-major SWIZZLE_128B
+// layout with SBO = 1024 B (next 8 pixels) and LBO = 8192 B (next 64 channels = next box).
+// One CTA owns (128 co) x (BN ci) x (T taps of one filter row) and a contiguous range of pixel patches (split-K);
+// T accumulators of BN fp32 columns live in TMEM; the epilogue adds them into dwp[tap][co][ci] with vector reds.
+// Two smem rings: A (shared by the T taps of a k-block) and B (one slot per tap).
+struct TcWgradParams {
+  float* dwp;            // [taps][Cout][Cin] fp32, zero-filled by the caller
+  int N, H, W, Cin, Cout;
+  int taps_w, dil;
+  int tiles_h, tiles_w;  // 4x16 pixel patches per image
+  int kb_per_split;      // pixel patches per CTA (grid.z splits)
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int BN, int T, int NPROD>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_constant__ CUtensorMap tm_dy_lo,
+                const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
+                const TcWgradParams p) {
+  constexpr int NSPLIT = NPROD == 3 ? 2 : 1;
+  constexpr int A_STAGE = NSPLIT * TC_A_BYTES;                 // 128 co x 64 px per plane
+  constexpr int B_PLANE = BN * TC_BLOCK_K * 2;
+  constexpr int B_STAGE = NSPLIT * B_PLANE;
+  constexpr int SA = 2;
+  constexpr int SB_RAW = (200 * 1024 - SA * A_STAGE) / B_STAGE;
+  constexpr int SB = SB_RAW > 6 ? 6 : SB_RAW;
+  static_assert(SB >= 2, "B ring too small");
+  constexpr int NCOLS = T * BN <= 32 ? 32 : T * BN <= 64 ? 64 : T * BN <= 128 ? 128 : T * BN <= 256 ? 256 : 512;
+  constexpr uint32_t IDESC = make_idesc_bf16_mn(128, BN);
+  constexpr int BOX_BYTES = 64 * 128;                          // one {64 c, 16 w, 4 h} box
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + SA * A_STAGE;
+  __shared__ __align__(8) uint64_t full_a[SA], empty_a[SA], full_b[SB], empty_b[SB];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ci_tiles = p.Cin / BN;
+  const int ci0 = (blockIdx.x % ci_tiles) * BN;
+  const int tap_row = blockIdx.x / ci_tiles;                   // filter row r (T == taps_w) or 0
+  const int co0 = blockIdx.y * 128;
+  const int total_kb = p.N * p.tiles_h * p.tiles_w;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(total_kb, kb_begin + p.kb_per_split);
+  const int num_kb = kb_end - kb_begin;
+  const int half = p.taps_w >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SA; ++s) { mbar_init(smem_u32(&full_a[s]), 1); mbar_init(smem_u32(&empty_a[s]), 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(smem_u32(&full_b[s]), 1); mbar_init(smem_u32(&empty_b[s]), 1); }
+    mbar_init(smem_u32(&tmem_full_bar), 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_dy_hi); tma_prefetch_desc(&tm_x_hi);
+    if (NSPLIT == 2) { tma_prefetch_desc(&tm_dy_lo); tma_prefetch_desc(&tm_x_lo); }
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(NCOLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (num_kb > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        for (int i = 0; i < num_kb; ++i) {
+          int kb = kb_begin + i;
+          const int tw = kb % p.tiles_w; kb /= p.tiles_w;
+          const int th = kb % p.tiles_h; const int n = kb / p.tiles_h;
+          const int h0 = th * 4, w0 = tw * 16;
+          const int sa = i % SA;
+          mbar_wait(smem_u32(&empty_a[sa]), ((i / SA) & 1) ^ 1);
+          const uint32_t bar_a = smem_u32(&full_a[sa]);
+          mbar_expect_tx(bar_a, A_STAGE);
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {      // channels co0+64..127 of a 64-channel tensor are out of bounds = zeros
+            tma_load_4d(smem_u32(smem_a + sa * A_STAGE + hf * BOX_BYTES), &tm_dy_hi, bar_a, co0 + 64 * hf, w0, h0, n);
+            if (NSPLIT == 2)
+              tma_load_4d(smem_u32(smem_a + sa * A_STAGE + TC_A_BYTES + hf * BOX_BYTES), &tm_dy_lo, bar_a, co0 + 64 * hf, w0, h0, n);
+          }
+#pragma unroll
+          for (int t = 0; t < T; ++t) {
+            const int j = i * T + t;
+            const int sb = j % SB;
+            mbar_wait(smem_u32(&empty_b[sb]), ((j / SB) & 1) ^ 1);
+            const int r = (T == 1) ? half : tap_row;            // 1x1: the only tap; 3x3: this CTA's filter row
+            const int sx = (T == 1) ? half : t;
+            const int hh = h0 + (r - half) * p.dil, ww = w0 + (sx - half) * p.dil;
+            const uint32_t bar_b = smem_u32(&full_b[sb]);
+            mbar_expect_tx(bar_b, B_STAGE);
+#pragma unroll
+            for (int part = 0; part < BN / 64; ++part) {
+              tma_load_4d(smem_u32(smem_b + sb * B_STAGE + part * BOX_BYTES), &tm_x_hi, bar_b, ci0 + 64 * part, ww, hh, n);
+              if (NSPLIT == 2)
+                tma_load_4d(smem_u32(smem_b + sb * B_STAGE + B_PLANE + part * BOX_BYTES), &tm_x_lo, bar_b, ci0 + 64 * part, ww, hh, n);
+            }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        for (int i = 0; i < num_kb; ++i) {
+          const int sa = i % SA;
+          mbar_wait(smem_u32(&full_a[sa]), (i / SA) & 1);
+          const uint32_t a_addr = smem_u32(smem_a + sa * A_STAGE);
+          const uint64_t a_hi = make_mnmajor_sw128_desc(a_addr, BOX_BYTES, 1024);
+          const uint64_t a_lo = make_mnmajor_sw128_desc(a_addr + TC_A_BYTES, BOX_BYTES, 1024);
+#pragma unroll
+          for (int t = 0; t < T; ++t) {
+            const int j = i * T + t;
+            const int sb = j % SB;
+            mbar_wait(smem_u32(&full_b[sb]), (j / SB) & 1);
+            tc_fence_after();
+            const uint32_t b_addr = smem_u32(smem_b + sb * B_STAGE);
+            const uint64_t b_hi = make_mnmajor_sw128_desc(b_addr, BOX_BYTES, 1024);
+            const uint64_t b_lo = make_mnmajor_sw128_desc(b_addr + B_PLANE, BOX_BYTES, 1024);
+            const uint32_t acc = tmem_base + (uint32_t)(t * BN);
+#pragma unroll
+            for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
+              const uint64_t adv = (uint64_t)((k * 16 * 128) >> 4);     // 16 pixels = 16 rows of 128 bytes along K
+              if (NPROD == 3) {
+                umma_bf16(acc, a_hi + adv, b_lo + adv, IDESC, (i | k) != 0);
+                umma_bf16(acc, a_lo + adv, b_hi + adv, IDESC, 1);
+                umma_bf16(acc, a_hi + adv, b_hi + adv, IDESC, 1);
+              } else {
+                umma_bf16(acc, a_hi + adv, b_hi + adv, IDESC, (i | k) != 0);
+              }
+            }
+            umma_commit(smem_u32(&empty_b[sb]));
+          }
+          umma_commit(smem_u32(&empty_a[sa]));
+        }
+        umma_commit(smem_u32(&tmem_full_bar));
+      }
+    } else {
+      const int q = warp & 3;
+      const int co = co0 + q * 32 + lane;
+      const bool co_ok = co < p.Cout;
+      mbar_wait(smem_u32(&tmem_full_bar), 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int t = 0; t < T; ++t) {
+        const int tap = (T == 1) ? 0 : tap_row * p.taps_w + t;
+        float* dst = p.dwp + ((size_t)tap * p.Cout + (co_ok ? co : 0)) * p.Cin + ci0;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * BN + c * 32), v);
+          if (co_ok)
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            red_add_v4(dst + c * 32 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(NCOLS));
+  }
+}
+
+// dwp[tap][co][ci] -> dw[co][ci][r][s]
+__global__ void unpack_wgrad_tc_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Cout, int Cin, int taps) {
+  const int64_t total = (int64_t)Cout * Cin * taps;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int tap = (int)(i % taps); int64_t q = i / taps;
+    int ci = (int)(q % Cin); int co = (int)(q / Cin);
+    dw[i] = dwp[((int64_t)tap * Cout + co) * Cin + ci];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ operand preparation
 // x fp32 -> hi = bf16(x), lo = bf16(x - hi)      (n multiple of 4)
 __global__ void split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
@@ -310,12 +513,12 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C) {
+static int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int box_h = TC_TH) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)"); return DDN_EUNSUPPORTED; }
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {TC_BLOCK_K, TC_TW, TC_TH, 1};
+  cuuint32_t box[4] = {TC_BLOCK_K, TC_TW, (cuuint32_t)box_h, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -337,6 +540,80 @@ static int make_weight_map(CUtensorMap* m, const void* base, int rows, int K, in
   return 0;
 }
 
+
+template <int BN, int T, int NPROD>
+static int launch_wgrad_tc(const CUtensorMap& dy_hi, const CUtensorMap& dy_lo, const CUtensorMap& x_hi, const CUtensorMap& x_lo,
+                           const TcWgradParams& p, int splits, cudaStream_t st) {
+  constexpr int NSPLIT = NPROD == 3 ? 2 : 1;
+  constexpr int A_STAGE = NSPLIT * TC_A_BYTES, B_STAGE = NSPLIT * BN * TC_BLOCK_K * 2;
+  constexpr int SB_RAW = (200 * 1024 - 2 * A_STAGE) / B_STAGE;
+  constexpr int SB = SB_RAW > 6 ? 6 : SB_RAW;
+  const size_t smem = (size_t)2 * A_STAGE + (size_t)SB * B_STAGE + 1024;
+  static bool configured = false;
+  if (!configured) {
+    DDN_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<BN, T, NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int tap_rows = (T == 1) ? 1 : p.taps_w;
+  dim3 grid((unsigned)((p.Cin / BN) * tap_rows), (unsigned)ceil_div(p.Cout, 128), (unsigned)splits);
+  DDN_LAUNCH((wgrad_tc_kernel<BN, T, NPROD>), grid, TC_THREADS, smem, st, dy_hi, dy_lo, x_hi, x_lo, p);
+  return 0;
+}
+
+// dw[Cout][Cin][k][k] (overwritten) from x [N,H,W,Cin] and dy [N,H,W,Cout], both fp32 NHWC.
+static int tc_wgrad(const float* x, const float* dy, float* dw, int N, int H, int W, int Cin, int Cout, int k, int dil,
+                    int precision, void* ws, size_t ws_bytes, float* dwp, cudaStream_t st) {
+  const size_t x_el = (size_t)N * H * W * Cin, dy_el = (size_t)N * H * W * Cout;
+  const size_t x_b = align_up(x_el * 2, 1024), dy_b = align_up(dy_el * 2, 1024);
+  char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<uintptr_t>(ws), 1024));
+  if ((size_t)(base - (char*)ws) + 2 * x_b + 2 * dy_b > ws_bytes) {
+    set_error("tcgen05 wgrad workspace too small (%zu needed)", 2 * x_b + 2 * dy_b + 1024);
+    return DDN_EWORKSPACE;
+  }
+  __nv_bfloat16* x_hi = (__nv_bfloat16*)base;
+  __nv_bfloat16* x_lo = (__nv_bfloat16*)(base + x_b);
+  __nv_bfloat16* dy_hi = (__nv_bfloat16*)(base + 2 * x_b);
+  __nv_bfloat16* dy_lo = (__nv_bfloat16*)(base + 2 * x_b + dy_b);
+  const int want_lo = precision == DDN_PRECISION_BF16X3;
+  {
+    int64_t n4 = (int64_t)(x_el / 4);
+    DDN_LAUNCH(split_bf16_kernel, (int)std::min<int64_t>(ceil_div(n4, 256), (int64_t)num_sms() * 8), 256, 0, st, x, x_hi, x_lo, n4, want_lo);
+    n4 = (int64_t)(dy_el / 4);
+    DDN_LAUNCH(split_bf16_kernel, (int)std::min<int64_t>(ceil_div(n4, 256), (int64_t)num_sms() * 8), 256, 0, st, dy, dy_hi, dy_lo, n4, want_lo);
+  }
+  const int taps = k * k;
+  DDN_TRY(launch_fill_zero(dwp, sizeof(float) * (size_t)taps * Cout * Cin, st));
+  const int bn = Cin % 128 == 0 ? 128 : 64;
+  CUtensorMap m_dy_hi, m_dy_lo, m_x_hi, m_x_lo;
+  DDN_TRY(make_act_map(&m_dy_hi, dy_hi, N, H, W, Cout, 4));
+  DDN_TRY(make_act_map(&m_dy_lo, want_lo ? dy_lo : dy_hi, N, H, W, Cout, 4));
+  DDN_TRY(make_act_map(&m_x_hi, x_hi, N, H, W, Cin, 4));
+  DDN_TRY(make_act_map(&m_x_lo, want_lo ? x_lo : x_hi, N, H, W, Cin, 4));
+  TcWgradParams p;
+  p.dwp = dwp; p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.taps_w = k; p.dil = dil;
+  p.tiles_h = (int)ceil_div(H, 4); p.tiles_w = (int)ceil_div(W, 16);
+  const int total_kb = N * p.tiles_h * p.tiles_w;
+  const int ctas_xy = (Cin / bn) * (k == 3 ? 3 : 1) * (int)ceil_div(Cout, 128);
+  int splits = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(2 * num_sms(), ctas_xy), ceil_div(total_kb, 8)));
+  p.kb_per_split = (int)ceil_div(total_kb, splits);
+  splits = (int)ceil_div(total_kb, p.kb_per_split);
+  const double fl = 2.0 * N * H * W * (double)Cout * taps * Cin;
+  {
+    ProfScope ps(PROF_CONV_WGRAD_TC, fl, st);
+#define WG(BNV, TV)                                                                                      \
+  do {                                                                                                   \
+    if (want_lo) DDN_TRY((launch_wgrad_tc<BNV, TV, 3>(m_dy_hi, m_dy_lo, m_x_hi, m_x_lo, p, splits, st))); \
+    else DDN_TRY((launch_wgrad_tc<BNV, TV, 1>(m_dy_hi, m_dy_lo, m_x_hi, m_x_lo, p, splits, st)));         \
+  } while (0)
+    if (k == 3) { if (bn == 128) WG(128, 3); else WG(64, 3); }
+    else { if (bn == 128) WG(128, 1); else WG(64, 1); }
+#undef WG
+  }
+  int blocks = (int)std::min<int64_t>(ceil_div((int64_t)taps * Cout * Cin, 256), 4096);
+  DDN_LAUNCH(unpack_wgrad_tc_kernel, blocks, 256, 0, st, dwp, dw, Cout, Cin, taps);
+  return 0;
+}
+
 bool tc_available() { return true; }
 
 bool tc_conv_supported(int Cin, int Cout, int k, int stride, int pad, int dil, int H, int W) {
@@ -350,7 +627,10 @@ bool tc_conv_supported(int Cin, int Cout, int k, int stride, int pad, int dil, i
 static const size_t kMaxWeightElems = (size_t)9 * 512 * 512;
 size_t tc_workspace_bytes(size_t max_act_elems) {
   // max_act_elems: the largest N*H*W*C tensor any supported conv reads (forward input or dY)
-  return 2 * align_up(max_act_elems * 2, 1024) + 2 * align_up(kMaxWeightElems * 2, 1024) + 2048;
+  // forward / dgrad: 2 activation planes + 2 weight planes; wgrad: 2 x planes + 2 dy planes
+  size_t fwd = 2 * align_up(max_act_elems * 2, 1024) + 2 * align_up(kMaxWeightElems * 2, 1024);
+  size_t wg = 4 * align_up(max_act_elems * 2, 1024);
+  return (fwd > wg ? fwd : wg) + 2048;
 }
 
 template <int BLOCK_N, int NPROD>
@@ -428,14 +708,9 @@ int tc_conv_backward(const float* x, const float* w, const float* dy, float* dx,
                      int N, int H, int W, int Cin, int Cout, int k, int pad, int dil, int precision,
                      void* ws, size_t ws_bytes, float* dwp_scratch, cudaStream_t st) {
   const double fl = 2.0 * N * H * W * (double)Cout * k * k * Cin;
-  ConvGeom g;
-  DDN_TRY(conv_geom_init(&g, N, H, W, Cin, H, W, Cout, k, k, 1, 1, pad, dil));
-  DDN_TRY(launch_fill_zero(dwp_scratch, sizeof(float) * (size_t)k * k * Cin * Cout, st));
-  {
-    ProfScope ps(PROF_CONV_WGRAD_SIMT, fl, st);
-    DDN_TRY(launch_conv_wgrad_f32(x, dy, dwp_scratch, g, st));
-  }
-  DDN_TRY(launch_unpack_wgrad(dwp_scratch, dw, Cout, Cin, Cin, k, k, st));
+  (void)fl; (void)pad;
+  // Cout = 64 (layer1) rides the same kernel: the 128-row A box reads channels 64..127 out of bounds = zeros
+  DDN_TRY(tc_wgrad(x, dy, dw, N, H, W, Cin, Cout, k, dil, precision, ws, ws_bytes, dwp_scratch, st));
   if (dx) DDN_TRY(tc_run(dy, w, dx, dx_addend, N, H, W, Cin, Cout, k, dil, 1, precision, ws, ws_bytes, st));
   return 0;
 }
