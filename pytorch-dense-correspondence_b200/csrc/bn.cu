@@ -74,17 +74,36 @@ bn_colsum_kernel(const float* __restrict__ x, const float* __restrict__ dy, cons
   }
 }
 
-__global__ void bn_stats_finalize_kernel(const float* __restrict__ partial, int nblk, int64_t M, int C,
-                                         float* __restrict__ mean, float* __restrict__ invstd,
-                                         float* __restrict__ running_mean, float* __restrict__ running_var,
-                                         float momentum, float eps) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0, ss = 0;
-  for (int b = 0; b < nblk; ++b) {
-    s += (double)partial[(int64_t)b * C + c];
-    ss += (double)partial[((int64_t)nblk + b) * C + c];
+// Column sums of the per-block partials in fp64: 32 channels x 8 slices per block (coalesced 128-byte rows),
+// so the serial chain per thread is nblk/8 instead of nblk.
+__device__ __forceinline__ void reduce_partials(const float* __restrict__ partial, int nblk, int C, int c, int slice,
+                                                double& s, double& ss) {
+  s = 0; ss = 0;
+  if (c < C) {
+    for (int b = slice; b < nblk; b += 8) {
+      s += (double)__ldg(partial + (int64_t)b * C + c);
+      ss += (double)__ldg(partial + ((int64_t)nblk + b) * C + c);
+    }
   }
+  __shared__ double sh[2][8][32];
+  const int lane = threadIdx.x & 31;
+  sh[0][slice][lane] = s; sh[1][slice][lane] = ss;
+  __syncthreads();
+  if (slice == 0) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { s += sh[0][k][lane]; ss += sh[1][k][lane]; }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_stats_finalize_kernel(const float* __restrict__ partial, int nblk, int64_t M, int C,
+                         float* __restrict__ mean, float* __restrict__ invstd,
+                         float* __restrict__ running_mean, float* __restrict__ running_var,
+                         float momentum, float eps) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), slice = threadIdx.x >> 5;
+  double s, ss;
+  reduce_partials(partial, nblk, C, c, slice, s, ss);
+  if (slice != 0 || c >= C) return;
   double mu = s / (double)M;
   double var = ss / (double)M - mu * mu;
   if (var < 0) var = 0;
@@ -136,15 +155,13 @@ bn_apply_kernel(BnApplyArgs a) {
   }
 }
 
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0, ss = 0;
-  for (int b = 0; b < nblk; ++b) {
-    s += (double)partial[(int64_t)b * C + c];
-    ss += (double)partial[((int64_t)nblk + b) * C + c];
-  }
+__global__ void __launch_bounds__(256)
+bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C,
+                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), slice = threadIdx.x >> 5;
+  double s, ss;
+  reduce_partials(partial, nblk, C, c, slice, s, ss);
+  if (slice != 0 || c >= C) return;
   dbeta[c] = (float)s;
   dgamma[c] = (float)ss;
 }
@@ -280,7 +297,7 @@ int launch_bn_stats(const float* x, int64_t M, int C, float* partial, float* mea
   int nblk = bn_partial_blocks(M, C);
   DDN_LAUNCH(bn_colsum_kernel<0>, nblk, BN_THREADS, 0, st, x, nullptr, nullptr, nullptr, nullptr, M, C,
              bn_rows_per_block(M, C), 0, partial);
-  DDN_LAUNCH(bn_stats_finalize_kernel, (int)ceil_div(C, 128), 128, 0, st, partial, nblk, M, C, mean, invstd,
+  DDN_LAUNCH(bn_stats_finalize_kernel, (int)ceil_div(C, 32), 256, 0, st, partial, nblk, M, C, mean, invstd,
              running_mean, running_var, momentum, eps);
   return 0;
 }
@@ -301,7 +318,7 @@ int launch_bn_backward(const BnBwdArgs& a, cudaStream_t st) {
   int nblk = bn_partial_blocks(a.M, a.C);
   DDN_LAUNCH(bn_colsum_kernel<1>, nblk, BN_THREADS, 0, st, a.x, a.dy, a.y, a.mean, a.invstd, a.M, a.C,
              bn_rows_per_block(a.M, a.C), a.relu, a.partial);
-  DDN_LAUNCH(bn_bwd_finalize_kernel, (int)ceil_div(a.C, 128), 128, 0, st, a.partial, nblk, a.C, a.dgamma, a.dbeta);
+  DDN_LAUNCH(bn_bwd_finalize_kernel, (int)ceil_div(a.C, 32), 256, 0, st, a.partial, nblk, a.C, a.dgamma, a.dbeta);
   DDN_LAUNCH(bn_bwd_apply_kernel, ew_blocks(a.M * (a.C / 4)), BN_THREADS, 5 * a.C * sizeof(float), st, a);
   return 0;
 }

@@ -594,7 +594,10 @@ static int tc_wgrad(const float* x, const float* dy, float* dw, int N, int H, in
   p.tiles_h = (int)ceil_div(H, 4); p.tiles_w = (int)ceil_div(W, 16);
   const int total_kb = N * p.tiles_h * p.tiles_w;
   const int ctas_xy = (Cin / bn) * (k == 3 ? 3 : 1) * (int)ceil_div(Cout, 128);
-  int splits = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(2 * num_sms(), ctas_xy), ceil_div(total_kb, 8)));
+  // split-K so that the grid is (just under) a whole number of waves: 1 CTA per SM resident, no ragged tail wave
+  const int sms = num_sms();
+  int waves = ctas_xy > sms ? 1 : (total_kb >= 64 * (sms / ctas_xy) ? 2 : 1);
+  int splits = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)waves * sms / ctas_xy, ceil_div(total_kb, 4)));
   p.kb_per_split = (int)ceil_div(total_kb, splits);
   splits = (int)ceil_div(total_kb, p.kb_per_split);
   const double fl = 2.0 * N * H * W * (double)Cout * taps * Cin;
