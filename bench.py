@@ -195,6 +195,17 @@ def run_ours(args):
     from pdc_b200 import _native as N, synthetic, loss_composer, data_parallel as DP
     from oracle import loss_oracle as LO      # only for DEFAULT_LOSS_CONFIG constants + the cpu_baseline leg
 
+    # stdout carries exactly ONE JSON line: anything a library prints while we run (NCCL's version banner ...) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(obj), flush=True)
+        os.dup2(2, 1)
+
     rank, world, local_rank = DP.init_from_env()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -264,7 +275,7 @@ def run_ours(args):
 
     if args.profile_run:
         if rank == 0:
-            print(json.dumps({"profile_run": True, "ms_per_step_under_profiler": ms_total / args.steps, "classes": prof}))
+            emit({"profile_run": True, "ms_per_step_under_profiler": ms_total / args.steps, "classes": prof})
         return
 
     # ---- timed region 2: end to end from pinned host memory, loss read back every step
@@ -333,7 +344,7 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "loss": float(loss.item()),
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

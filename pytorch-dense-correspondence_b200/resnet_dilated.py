@@ -82,8 +82,21 @@ class _Backbone(torch.autograd.Function):
         N.check(N.lib.ddn_resnet34_8s_backward(N.ptr(dy), N.ptr(flat), N.ptr(grads), N.ptr(ctx.ws), ctx.ws.numel(),
                                                B, H, W, D, _BN_EPS, ctx.prec, N.stream_ptr()))
         ctx.ws = None
-        views = tuple(grads[o:o + n].view(s) for (_, s, o, n) in owner._ptab)
-        return (None, None) + views
+        # Gradients are accumulated by THIS function into one flat array that every p.grad aliases (like a fused
+        # "main_grad"): the second backward of a step (image B, then image A) is one flat add instead of 110 small
+        # AccumulateGrad kernels, and the data-parallel all-reduce / a fused optimizer see a single buffer.
+        ps = owner._params
+        fg = owner._flat_grad
+        fresh = (fg is None or ps[0].grad is None or ps[-1].grad is None or fg.device != grads.device or
+                 ps[0].grad.data_ptr() != fg.data_ptr() + 4 * owner._ptab[0][2] or
+                 ps[-1].grad.data_ptr() != fg.data_ptr() + 4 * owner._ptab[-1][2])
+        if fresh:                      # first backward since zero_grad(set_to_none=True)
+            owner._flat_grad = grads
+            for p, (_, s, o, n) in zip(ps, owner._ptab):
+                p.grad = grads[o:o + n].view(s)
+        else:
+            fg.add_(grads)
+        return (None, None) + (None,) * len(ps)
 
 
 class Resnet34_8s(nn.Module):
@@ -100,6 +113,7 @@ class Resnet34_8s(nn.Module):
         self._flat = torch.zeros(n_params, dtype=torch.float32)
         self._flat_bufs = torch.zeros(n_bufs, dtype=torch.float32)
         self._flat_version = 0
+        self._flat_grad = None
         self._params = []
         self._nbt = []
         root = _Holder()
@@ -197,6 +211,13 @@ class Resnet34_8s(nn.Module):
         else:
             self._flat = self._flat.to(dev)   # CPU copy only serves state_dict round trips
         return out
+
+    @property
+    def flat_gradient(self):
+        """The flat fp32 array all ``p.grad`` alias after a backward (None before the first one / after zero_grad)."""
+        if self._flat_grad is None or self._params[0].grad is None:
+            return None
+        return self._flat_grad
 
     @property
     def flat_parameters(self):
