@@ -11,6 +11,20 @@ namespace ddn {
 
 constexpr int BN_THREADS = 256;
 
+// x -> (hi, lo) bf16 with x ~= hi + lo; 4 values -> two 8-byte stores
+__device__ __forceinline__ void store_split4(__nv_bfloat16* hi, __nv_bfloat16* lo, int64_t i4, float4 v) {
+  __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z), h3 = __float2bfloat16_rn(v.w);
+  __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
+  uint2 ho; ho.x = *reinterpret_cast<uint32_t*>(&a); ho.y = *reinterpret_cast<uint32_t*>(&b);
+  reinterpret_cast<uint2*>(hi)[i4] = ho;
+  if (lo) {
+    __nv_bfloat162 c = __halves2bfloat162(__float2bfloat16_rn(v.x - __bfloat162float(h0)), __float2bfloat16_rn(v.y - __bfloat162float(h1)));
+    __nv_bfloat162 d = __halves2bfloat162(__float2bfloat16_rn(v.z - __bfloat162float(h2)), __float2bfloat16_rn(v.w - __bfloat162float(h3)));
+    uint2 l2; l2.x = *reinterpret_cast<uint32_t*>(&c); l2.y = *reinterpret_cast<uint32_t*>(&d);
+    reinterpret_cast<uint2*>(lo)[i4] = l2;
+  }
+}
+
 static inline int bn_rows_per_iter(int C) { return BN_THREADS / (C / 4); }
 
 int bn_partial_blocks(int64_t M, int C) {
@@ -152,6 +166,7 @@ bn_apply_kernel(BnApplyArgs a) {
     }
     if (a.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
     reinterpret_cast<float4*>(a.y)[i] = v;
+    if (a.hi) store_split4(a.hi, a.lo, i, v);
   }
 }
 
@@ -194,7 +209,8 @@ bn_bwd_apply_kernel(BnBwdArgs a) {
     d.y = k1[c + 1] * (g.y - mb[c + 1] - (v.y - mu[c + 1]) * is[c + 1] * mg[c + 1]);
     d.z = k1[c + 2] * (g.z - mb[c + 2] - (v.z - mu[c + 2]) * is[c + 2] * mg[c + 2]);
     d.w = k1[c + 3] * (g.w - mb[c + 3] - (v.w - mu[c + 3]) * is[c + 3] * mg[c + 3]);
-    reinterpret_cast<float4*>(a.dx)[i] = d;
+    if (a.dx) reinterpret_cast<float4*>(a.dx)[i] = d;
+    if (a.dx_hi) store_split4(a.dx_hi, a.dx_lo, i, d);
   }
 }
 
@@ -203,7 +219,8 @@ bn_bwd_apply_kernel(BnBwdArgs a) {
 __global__ void __launch_bounds__(256)
 stem_bn_relu_pool_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
                          const float* __restrict__ gamma, const float* __restrict__ beta,
-                         float* __restrict__ y, uint8_t* __restrict__ argmax, int N, int Hc, int Wc, int C, int Hp, int Wp) {
+                         float* __restrict__ y, uint8_t* __restrict__ argmax, __nv_bfloat16* __restrict__ y_hi,
+                         __nv_bfloat16* __restrict__ y_lo, int N, int Hc, int Wc, int C, int Hp, int Wp) {
   const int q = C >> 2;
   const int64_t total = (int64_t)N * Hp * Wp * q;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -235,6 +252,7 @@ stem_bn_relu_pool_kernel(const float* __restrict__ x, const float* __restrict__ 
     }
     reinterpret_cast<float4*>(y)[i] = best;
     reinterpret_cast<uchar4*>(argmax)[i] = arg;
+    if (y_hi) store_split4(y_hi, y_lo, i, best);
   }
 }
 
@@ -302,6 +320,13 @@ int launch_bn_stats(const float* x, int64_t M, int C, float* partial, float* mea
   return 0;
 }
 
+int launch_bn_stats_finalize(const float* partial, int nblk, int64_t M, int C, float* mean, float* invstd,
+                             float* running_mean, float* running_var, float momentum, float eps, cudaStream_t st) {
+  DDN_LAUNCH(bn_stats_finalize_kernel, (int)ceil_div(C, 32), 256, 0, st, partial, nblk, M, C, mean, invstd,
+             running_mean, running_var, momentum, eps);
+  return 0;
+}
+
 int launch_bn_eval_stats(const float* rm, const float* rv, int C, float eps, float* mean, float* invstd, cudaStream_t st) {
   DDN_LAUNCH(bn_eval_stats_kernel, (int)ceil_div(C, 128), 128, 0, st, rm, rv, C, eps, mean, invstd);
   return 0;
@@ -324,10 +349,11 @@ int launch_bn_backward(const BnBwdArgs& a, cudaStream_t st) {
 }
 
 int launch_stem_bn_relu_pool(const float* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
-                             float* y, uint8_t* argmax, int N, int Hc, int Wc, int C, cudaStream_t st) {
+                             float* y, uint8_t* argmax, __nv_bfloat16* y_hi, __nv_bfloat16* y_lo,
+                             int N, int Hc, int Wc, int C, cudaStream_t st) {
   int Hp = (Hc - 1) / 2 + 1, Wp = (Wc - 1) / 2 + 1;
   int64_t total = (int64_t)N * Hp * Wp * (C / 4);
-  DDN_LAUNCH(stem_bn_relu_pool_kernel, ew_blocks(total), 256, 0, st, x, mean, invstd, gamma, beta, y, argmax, N, Hc, Wc, C, Hp, Wp);
+  DDN_LAUNCH(stem_bn_relu_pool_kernel, ew_blocks(total), 256, 0, st, x, mean, invstd, gamma, beta, y, argmax, y_hi, y_lo, N, Hc, Wc, C, Hp, Wp);
   return 0;
 }
 

@@ -27,6 +27,8 @@ int launch_conv_wgrad_f32(const float* in, const float* dy, float* dwp, const Co
 int bn_partial_blocks(int64_t M, int C);
 int launch_bn_stats(const float* x, int64_t M, int C, float* partial, float* mean, float* invstd,
                     float* running_mean, float* running_var, float momentum, float eps, cudaStream_t st);
+int launch_bn_stats_finalize(const float* partial, int nblk, int64_t M, int C, float* mean, float* invstd,
+                             float* running_mean, float* running_var, float momentum, float eps, cudaStream_t st);
 int launch_bn_eval_stats(const float* running_mean, const float* running_var, int C, float eps,
                          float* mean, float* invstd, cudaStream_t st);
 // y = relu?( (x-mean)*invstd*gamma+beta + res ), res = r (identity) or (r-rmean)*rinvstd*rgamma+rbeta
@@ -34,18 +36,21 @@ struct BnApplyArgs {
   const float* x; const float* mean; const float* invstd; const float* gamma; const float* beta;
   const float* r; const float* rmean; const float* rinvstd; const float* rgamma; const float* rbeta;
   float* y; int64_t M; int C; int relu;
+  __nv_bfloat16* hi; __nv_bfloat16* lo;   // optional: also emit y as bf16 hi/lo planes (tensor-core operands)
 };
 int launch_bn_apply(const BnApplyArgs& a, cudaStream_t st);
 // backward of y = relu?(bn(x) + res): g = dy*(y>0); sums -> dgamma,dbeta; dx; optional g_out (= d res)
 struct BnBwdArgs {
   const float* dy; const float* y; const float* x; const float* mean; const float* invstd; const float* gamma;
   float* dx; float* dgamma; float* dbeta; float* g_out; float* partial; int64_t M; int C; int relu; int training;
+  __nv_bfloat16* dx_hi; __nv_bfloat16* dx_lo;   // optional: emit dx as bf16 hi/lo planes (dx itself may then be null)
 };
 int launch_bn_backward(const BnBwdArgs& a, cudaStream_t st);
 
 // stem: conv1 raw [N,Hc,Wc,64] -> bn+relu+maxpool3x3/2 -> y [N,Hp,Wp,64], argmax uint8
 int launch_stem_bn_relu_pool(const float* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
-                             float* y, uint8_t* argmax, int N, int Hc, int Wc, int C, cudaStream_t st);
+                             float* y, uint8_t* argmax, __nv_bfloat16* y_hi, __nv_bfloat16* y_lo,
+                             int N, int Hc, int Wc, int C, cudaStream_t st);
 // dy_pool [N,Hp,Wp,C] -> g [N,Hc,Wc,C] = d(relu out) * (bn(x) > 0)   (pre-BN-backward gradient)
 int launch_stem_pool_relu_backward(const float* dy_pool, const uint8_t* argmax, const float* x, const float* mean,
                                    const float* invstd, const float* gamma, const float* beta, float* g,

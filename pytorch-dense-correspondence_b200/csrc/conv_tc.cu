@@ -129,7 +129,22 @@ struct TcConvParams {
   int taps_w;            // 1 or 3 (k x k filter)
   int dil;
   int tiles_h, tiles_w;
+  float* bn_partial;     // optional [2][gridDim.x][Cout]: per-tile column sums / sums of squares of the conv output
 };
+
+// After the call, a[0] on lane l holds the sum over the 32 lanes of column l (butterfly reduce-scatter, 31 shuffles).
+__device__ __forceinline__ void warp_colsum32(float (&a)[32], int lane) {
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool up = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float keep = up ? a[i + half] : a[i];
+      const float send = up ? a[i] : a[i + half];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+}
 
 template <int BLOCK_N, int NPROD>   // NPROD = 1 (bf16) or 3 (bf16x3)
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -149,6 +164,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_part[2][4][BLOCK_N];      // BN partial sums of the 4 epilogue warps
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // tile coordinates
@@ -252,8 +268,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           *reinterpret_cast<float4*>(o + c * 32 + j) = f;
         }
       }
+      if (p.bn_partial) {      // tile rows outside the image hold garbage (their shifted taps can read valid pixels): mask
+        float a[32], b[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { a[j] = ok ? __uint_as_float(v[j]) : 0.f; b[j] = a[j] * a[j]; }
+        warp_colsum32(a, lane);
+        warp_colsum32(b, lane);
+        s_part[0][q][c * 32 + lane] = a[0];
+        s_part[1][q][c * 32 + lane] = b[0];
+      }
     }
     tc_fence_before();
+    if (p.bn_partial) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");          // the 4 epilogue warps only
+      const int e = threadIdx.x - 64;
+      if (e < BLOCK_N) {
+        const float s0 = s_part[0][0][e] + s_part[0][1][e] + s_part[0][2][e] + s_part[0][3][e];
+        const float s1 = s_part[1][0][e] + s_part[1][1][e] + s_part[1][2][e] + s_part[1][3][e];
+        const size_t nblk = gridDim.x;
+        p.bn_partial[(size_t)blockIdx.x * p.Cout + co0 + e] = s0;
+        p.bn_partial[(nblk + blockIdx.x) * p.Cout + co0 + e] = s1;
+      }
+    }
   }
   __syncthreads();
   if (warp == 1) {
@@ -560,35 +596,18 @@ static int launch_wgrad_tc(const CUtensorMap& dy_hi, const CUtensorMap& dy_lo, c
   return 0;
 }
 
-// dw[Cout][Cin][k][k] (overwritten) from x [N,H,W,Cin] and dy [N,H,W,Cout], both fp32 NHWC.
-static int tc_wgrad(const float* x, const float* dy, float* dw, int N, int H, int W, int Cin, int Cout, int k, int dil,
-                    int precision, void* ws, size_t ws_bytes, float* dwp, cudaStream_t st) {
-  const size_t x_el = (size_t)N * H * W * Cin, dy_el = (size_t)N * H * W * Cout;
-  const size_t x_b = align_up(x_el * 2, 1024), dy_b = align_up(dy_el * 2, 1024);
-  char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<uintptr_t>(ws), 1024));
-  if ((size_t)(base - (char*)ws) + 2 * x_b + 2 * dy_b > ws_bytes) {
-    set_error("tcgen05 wgrad workspace too small (%zu needed)", 2 * x_b + 2 * dy_b + 1024);
-    return DDN_EWORKSPACE;
-  }
-  __nv_bfloat16* x_hi = (__nv_bfloat16*)base;
-  __nv_bfloat16* x_lo = (__nv_bfloat16*)(base + x_b);
-  __nv_bfloat16* dy_hi = (__nv_bfloat16*)(base + 2 * x_b);
-  __nv_bfloat16* dy_lo = (__nv_bfloat16*)(base + 2 * x_b + dy_b);
+// dw[Cout][Cin][k][k] (overwritten) from the bf16 planes of x [N,H,W,Cin] and dy [N,H,W,Cout].
+int tc_wgrad_planes(TcPlanes x, TcPlanes dy, float* dw, int N, int H, int W, int Cin, int Cout, int k, int dil,
+                    int precision, float* dwp, cudaStream_t st) {
   const int want_lo = precision == DDN_PRECISION_BF16X3;
-  {
-    int64_t n4 = (int64_t)(x_el / 4);
-    DDN_LAUNCH(split_bf16_kernel, (int)std::min<int64_t>(ceil_div(n4, 256), (int64_t)num_sms() * 8), 256, 0, st, x, x_hi, x_lo, n4, want_lo);
-    n4 = (int64_t)(dy_el / 4);
-    DDN_LAUNCH(split_bf16_kernel, (int)std::min<int64_t>(ceil_div(n4, 256), (int64_t)num_sms() * 8), 256, 0, st, dy, dy_hi, dy_lo, n4, want_lo);
-  }
   const int taps = k * k;
   DDN_TRY(launch_fill_zero(dwp, sizeof(float) * (size_t)taps * Cout * Cin, st));
   const int bn = Cin % 128 == 0 ? 128 : 64;
   CUtensorMap m_dy_hi, m_dy_lo, m_x_hi, m_x_lo;
-  DDN_TRY(make_act_map(&m_dy_hi, dy_hi, N, H, W, Cout, 4));
-  DDN_TRY(make_act_map(&m_dy_lo, want_lo ? dy_lo : dy_hi, N, H, W, Cout, 4));
-  DDN_TRY(make_act_map(&m_x_hi, x_hi, N, H, W, Cin, 4));
-  DDN_TRY(make_act_map(&m_x_lo, want_lo ? x_lo : x_hi, N, H, W, Cin, 4));
+  DDN_TRY(make_act_map(&m_dy_hi, dy.hi, N, H, W, Cout, 4));
+  DDN_TRY(make_act_map(&m_dy_lo, want_lo ? dy.lo : dy.hi, N, H, W, Cout, 4));
+  DDN_TRY(make_act_map(&m_x_hi, x.hi, N, H, W, Cin, 4));
+  DDN_TRY(make_act_map(&m_x_lo, want_lo ? x.lo : x.hi, N, H, W, Cin, 4));
   TcWgradParams p;
   p.dwp = dwp; p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.taps_w = k; p.dil = dil;
   p.tiles_h = (int)ceil_div(H, 4); p.tiles_w = (int)ceil_div(W, 16);
@@ -620,20 +639,23 @@ static int tc_wgrad(const float* x, const float* dy, float* dw, int N, int H, in
 bool tc_available() { return true; }
 
 bool tc_conv_supported(int Cin, int Cout, int k, int stride, int pad, int dil, int H, int W) {
+  (void)H; (void)W;
   if (stride != 1 || Cin % 64 || Cout % 64) return false;
   if (k == 3) return pad == dil;
   if (k == 1) return pad == 0;
   return false;
 }
 
-// staging layout inside the tc workspace: act_hi | act_lo | w_hi | w_lo
 static const size_t kMaxWeightElems = (size_t)9 * 512 * 512;
-size_t tc_workspace_bytes(size_t max_act_elems) {
-  // max_act_elems: the largest N*H*W*C tensor any supported conv reads (forward input or dY)
-  // forward / dgrad: 2 activation planes + 2 weight planes; wgrad: 2 x planes + 2 dy planes
-  size_t fwd = 2 * align_up(max_act_elems * 2, 1024) + 2 * align_up(kMaxWeightElems * 2, 1024);
-  size_t wg = 4 * align_up(max_act_elems * 2, 1024);
-  return (fwd > wg ? fwd : wg) + 2048;
+size_t tc_weight_ws_bytes() { return 2 * align_up(kMaxWeightElems * 2, 1024) + 2048; }
+int tc_bn_partial_blocks(int N, int H, int W) { return N * (int)ceil_div(H, TC_TH) * (int)ceil_div(W, TC_TW); }
+
+int tc_split(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t n, int precision, cudaStream_t st) {
+  DDN_CHECK_ARG(n % 4 == 0, "split: element count must be a multiple of 4");
+  int64_t n4 = n / 4;
+  int blocks = (int)std::min<int64_t>(ceil_div(n4, 256), (int64_t)num_sms() * 8);
+  DDN_LAUNCH(split_bf16_kernel, blocks, 256, 0, st, x, hi, lo, n4, precision == DDN_PRECISION_BF16X3 ? 1 : 0);
+  return 0;
 }
 
 template <int BLOCK_N, int NPROD>
@@ -653,44 +675,34 @@ static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUt
   return 0;
 }
 
-// out[N,H,W,Cout] = conv(in[N,H,W,Cin]; packed weights) (+ addend); weights come in the reference layout and are
-// packed for the forward (dgrad = 0) or the data-gradient (dgrad = 1; then Cin/Cout are those of the ORIGINAL conv and
-// `in` is dY [N,H,W,Cout], `out` is dX [N,H,W,Cin]).
-static int tc_run(const float* in, const float* w_oihw, float* out, const float* addend, int N, int H, int W,
-                  int Cin, int Cout, int k, int dil, int dgrad, int precision, void* ws, size_t ws_bytes, cudaStream_t st) {
+// out[N,H,W,gout] = conv(planes of in[N,H,W,gin]; weights packed on the fly) (+ addend).  dgrad = 0: forward
+// (gin = Cin, gout = Cout).  dgrad = 1: data gradient (`in` = dY planes with Cout channels, out = dX with Cin channels;
+// Cin/Cout are those of the ORIGINAL conv).  bn_partial (forward only): [2][tc_bn_partial_blocks][Cout] column sums.
+int tc_conv_planes(TcPlanes in, const float* w_oihw, float* out, const float* addend, float* bn_partial,
+                   int N, int H, int W, int Cin, int Cout, int k, int dil, int dgrad, int precision,
+                   void* wws, size_t wws_bytes, cudaStream_t st) {
   const double fl = 2.0 * N * H * W * (double)Cout * k * k * Cin;
-  const int gin = dgrad ? Cout : Cin, gout = dgrad ? Cin : Cout;     // channels of the GEMM's input / output tensors
-  const size_t act = (size_t)N * H * W * gin;
+  const int gin = dgrad ? Cout : Cin, gout = dgrad ? Cin : Cout;
   const size_t wel = (size_t)Cout * Cin * k * k;
-  const size_t act_b = align_up(act * 2, 1024), w_b = align_up(kMaxWeightElems * 2, 1024);
-  DDN_CHECK_ARG(ws != nullptr, "tc workspace missing");
-  char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<uintptr_t>(ws), 1024));
-  if ((size_t)(base - (char*)ws) + 2 * act_b + 2 * w_b > ws_bytes) {
-    set_error("tcgen05 conv workspace too small (%zu needed)", 2 * act_b + 2 * w_b + 1024);
-    return DDN_EWORKSPACE;
-  }
-  DDN_CHECK_ARG(wel <= kMaxWeightElems, "weight tensor larger than the staging buffer");
-  __nv_bfloat16* a_hi = (__nv_bfloat16*)base;
-  __nv_bfloat16* a_lo = (__nv_bfloat16*)(base + act_b);
-  __nv_bfloat16* b_hi = (__nv_bfloat16*)(base + 2 * act_b);
-  __nv_bfloat16* b_lo = (__nv_bfloat16*)(base + 2 * act_b + w_b);
+  const size_t w_b = align_up(kMaxWeightElems * 2, 1024);
+  DDN_CHECK_ARG(wws != nullptr && wel <= kMaxWeightElems, "tc weight staging missing or weight tensor too large");
+  char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<uintptr_t>(wws), 1024));
+  if ((size_t)(base - (char*)wws) + 2 * w_b > wws_bytes) { set_error("tcgen05 weight staging too small"); return DDN_EWORKSPACE; }
+  __nv_bfloat16* b_hi = (__nv_bfloat16*)base;
+  __nv_bfloat16* b_lo = (__nv_bfloat16*)(base + w_b);
   const int want_lo = precision == DDN_PRECISION_BF16X3;
-  {
-    int64_t n4 = (int64_t)(act / 4);
-    int blocks = (int)std::min<int64_t>(ceil_div(n4, 256), (int64_t)num_sms() * 8);
-    DDN_LAUNCH(split_bf16_kernel, blocks, 256, 0, st, in, a_hi, a_lo, n4, want_lo);
-    int wblocks = (int)std::min<int64_t>(ceil_div((int64_t)wel, 256), 4096);
-    DDN_LAUNCH(pack_weights_tc_kernel, wblocks, 256, 0, st, w_oihw, b_hi, b_lo, Cout, Cin, k, dgrad, want_lo);
-  }
+  int wblocks = (int)std::min<int64_t>(ceil_div((int64_t)wel, 256), 4096);
+  DDN_LAUNCH(pack_weights_tc_kernel, wblocks, 256, 0, st, w_oihw, b_hi, b_lo, Cout, Cin, k, dgrad, want_lo);
   const int block_n = gout % 128 == 0 ? 128 : 64;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  DDN_TRY(make_act_map(&ma_hi, a_hi, N, H, W, gin));
-  DDN_TRY(make_act_map(&ma_lo, want_lo ? a_lo : a_hi, N, H, W, gin));
+  DDN_TRY(make_act_map(&ma_hi, in.hi, N, H, W, gin));
+  DDN_TRY(make_act_map(&ma_lo, want_lo ? in.lo : in.hi, N, H, W, gin));
   DDN_TRY(make_weight_map(&mb_hi, b_hi, gout, k * k * gin, block_n));
   DDN_TRY(make_weight_map(&mb_lo, want_lo ? b_lo : b_hi, gout, k * k * gin, block_n));
   TcConvParams p;
   p.out = out; p.addend = addend; p.N = N; p.H = H; p.W = W; p.Cin = gin; p.Cout = gout; p.taps_w = k; p.dil = dil;
   p.tiles_h = (int)ceil_div(H, TC_TH); p.tiles_w = (int)ceil_div(W, TC_TW);
+  p.bn_partial = bn_partial;
   ProfScope ps(dgrad ? PROF_CONV_DGRAD_TC : PROF_CONV_FWD_TC, fl, st);   // times the MMA kernel only
   if (want_lo) {
     if (block_n == 128) return launch_tc<128, 3>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);
@@ -700,21 +712,40 @@ static int tc_run(const float* in, const float* w_oihw, float* out, const float*
   return launch_tc<64, 1>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);
 }
 
+// ---- fp32-tensor wrappers (single-operator C ABI): split into the staging region, then run the plane kernels
+// staging layout: [weights hi|lo][x hi|lo][dy hi|lo]
+size_t tc_workspace_bytes(size_t max_act_elems) { return tc_weight_ws_bytes() + 4 * align_up(max_act_elems * 2, 1024) + 2048; }
+
+static int stage_planes(void* ws, size_t ws_bytes, size_t x_el, size_t dy_el, void** wws, TcPlanes* x, TcPlanes* dy) {
+  char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<uintptr_t>(ws), 1024));
+  const size_t wb = tc_weight_ws_bytes(), xb = align_up(x_el * 2, 1024), yb = align_up(dy_el * 2, 1024);
+  if ((size_t)(base - (char*)ws) + wb + 2 * xb + 2 * yb > ws_bytes) { set_error("tcgen05 staging workspace too small"); return DDN_EWORKSPACE; }
+  *wws = base;
+  char* q = base + align_up(wb, 1024);
+  x->hi = (__nv_bfloat16*)q; x->lo = (__nv_bfloat16*)(q + xb);
+  dy->hi = (__nv_bfloat16*)(q + 2 * xb); dy->lo = (__nv_bfloat16*)(q + 2 * xb + yb);
+  return 0;
+}
+
 int tc_conv_forward(const float* x, const float* w, float* y, int N, int H, int W, int Cin, int Cout, int k, int pad, int dil,
                     int precision, void* ws, size_t ws_bytes, cudaStream_t st) {
   (void)pad;
-  return tc_run(x, w, y, nullptr, N, H, W, Cin, Cout, k, dil, 0, precision, ws, ws_bytes, st);
+  void* wws; TcPlanes px, pdy;
+  DDN_TRY(stage_planes(ws, ws_bytes, (size_t)N * H * W * Cin, 0, &wws, &px, &pdy));
+  DDN_TRY(tc_split(x, const_cast<__nv_bfloat16*>(px.hi), const_cast<__nv_bfloat16*>(px.lo), (int64_t)N * H * W * Cin, precision, st));
+  return tc_conv_planes(px, w, y, nullptr, nullptr, N, H, W, Cin, Cout, k, dil, 0, precision, wws, tc_weight_ws_bytes(), st);
 }
 
-// data gradient on the tensor cores; weight gradient on the fp32 SIMT kernel for now (dwp_scratch: K x Cout floats)
 int tc_conv_backward(const float* x, const float* w, const float* dy, float* dx, const float* dx_addend, float* dw,
                      int N, int H, int W, int Cin, int Cout, int k, int pad, int dil, int precision,
                      void* ws, size_t ws_bytes, float* dwp_scratch, cudaStream_t st) {
-  const double fl = 2.0 * N * H * W * (double)Cout * k * k * Cin;
-  (void)fl; (void)pad;
-  // Cout = 64 (layer1) rides the same kernel: the 128-row A box reads channels 64..127 out of bounds = zeros
-  DDN_TRY(tc_wgrad(x, dy, dw, N, H, W, Cin, Cout, k, dil, precision, ws, ws_bytes, dwp_scratch, st));
-  if (dx) DDN_TRY(tc_run(dy, w, dx, dx_addend, N, H, W, Cin, Cout, k, dil, 1, precision, ws, ws_bytes, st));
+  (void)pad;
+  void* wws; TcPlanes px, pdy;
+  DDN_TRY(stage_planes(ws, ws_bytes, (size_t)N * H * W * Cin, (size_t)N * H * W * Cout, &wws, &px, &pdy));
+  DDN_TRY(tc_split(x, const_cast<__nv_bfloat16*>(px.hi), const_cast<__nv_bfloat16*>(px.lo), (int64_t)N * H * W * Cin, precision, st));
+  DDN_TRY(tc_split(dy, const_cast<__nv_bfloat16*>(pdy.hi), const_cast<__nv_bfloat16*>(pdy.lo), (int64_t)N * H * W * Cout, precision, st));
+  DDN_TRY(tc_wgrad_planes(px, pdy, dw, N, H, W, Cin, Cout, k, dil, precision, dwp_scratch, st));
+  if (dx) DDN_TRY(tc_conv_planes(pdy, w, dx, dx_addend, nullptr, N, H, W, Cin, Cout, k, dil, 1, precision, wws, tc_weight_ws_bytes(), st));
   return 0;
 }
 

@@ -152,17 +152,19 @@ static const NetSpec& get_spec(int D) {
 
 // ------------------------------------------------------------------------------------------------ workspace plan
 struct ConvBufs { size_t raw, mean, invstd; int Hin, Win, Hout, Wout; };
-struct BlockBufs { ConvBufs c1, c2, ds; size_t act1, out; };
+struct PlaneBufs { size_t hi, lo; };   // bf16 operand planes of an activation (tensor-core modes only)
+struct BlockBufs { ConvBufs c1, c2, ds; size_t act1, out; PlaneBufs act1_p, out_p; };
 struct Plan {
   int B, H, W, D, training, precision;
   int H1, W1, Hp, Wp;
   size_t x4, stem_raw, stem_mean, stem_invstd, pool_out, argmax;
+  PlaneBufs pool_p, grad_p;           // planes of the pooled stem output; planes of the current d(raw conv output)
+  size_t wws;                         // packed-weight staging of the tensor-core convs
+  bool tc;
   std::vector<BlockBufs> blk;
   size_t low, dlow;
   size_t wpack, wpack2, dwp, partial, scratch[4];
   size_t scratch_elems;
-  size_t tc;   // tensor-core staging region (bf16 hi/lo planes etc.)
-  size_t tc_bytes;
   size_t total;
 };
 
@@ -186,6 +188,9 @@ static int make_plan(Plan* p, int B, int H, int W, int D, int training, int prec
   p->stem_mean = f32(64); p->stem_invstd = f32(64);
   p->pool_out = f32((int64_t)B * p->Hp * p->Wp * 64);
   p->argmax = alloc((size_t)B * p->Hp * p->Wp * 64);
+  p->tc = precision != DDN_PRECISION_FP32_SIMT;
+  auto planes = [&](int64_t n) { PlaneBufs pb{0, 0}; if (p->tc) { pb.hi = alloc(2 * (size_t)n); pb.lo = alloc(2 * (size_t)n); } return pb; };
+  p->pool_p = planes((int64_t)B * p->Hp * p->Wp * 64);
   int h = p->Hp, w = p->Wp;
   size_t max_w = 0;
   int64_t max_act = (int64_t)B * p->H1 * p->W1 * 64;
@@ -204,9 +209,11 @@ static int make_plan(Plan* p, int B, int H, int W, int D, int training, int prec
     };
     bb.c1 = conv_bufs(b.c1, h, w);
     bb.act1 = f32((int64_t)B * bb.c1.Hout * bb.c1.Wout * b.c1.cout);
+    bb.act1_p = planes((int64_t)B * bb.c1.Hout * bb.c1.Wout * b.c1.cout);
     bb.c2 = conv_bufs(b.c2, bb.c1.Hout, bb.c1.Wout);
     if (b.has_ds) bb.ds = conv_bufs(b.ds, h, w);
     bb.out = f32((int64_t)B * bb.c2.Hout * bb.c2.Wout * b.c2.cout);
+    bb.out_p = planes((int64_t)B * bb.c2.Hout * bb.c2.Wout * b.c2.cout);
     h = bb.c2.Hout; w = bb.c2.Wout;
     p->blk.push_back(bb);
   }
@@ -219,12 +226,14 @@ static int make_plan(Plan* p, int B, int H, int W, int D, int training, int prec
   for (int C : {64, 128, 256, 512}) {
     int64_t Mmax = C == 64 ? (int64_t)B * p->H1 * p->W1 : (int64_t)B * p->Hp * p->Wp;
     max_partial = std::max<int64_t>(max_partial, 2ll * bn_partial_blocks(Mmax, C) * C + 2 * C);
+    int hh = C == 64 ? p->Hp : p->Hp / 2, ww = C == 64 ? p->Wp : p->Wp / 2;     // tcgen05 convs write one row per 8x16 tile
+    max_partial = std::max<int64_t>(max_partial, 2ll * tc_bn_partial_blocks(B, hh, ww) * C + 2 * C);
   }
   p->partial = f32(max_partial * 2);
   p->scratch_elems = (size_t)max_act;
   for (int i = 0; i < 4; ++i) p->scratch[i] = f32((int64_t)max_act);
-  p->tc_bytes = precision == DDN_PRECISION_FP32_SIMT ? 0 : tc_workspace_bytes((size_t)max_act);
-  p->tc = alloc(p->tc_bytes);
+  p->grad_p = planes(max_act);
+  p->wws = alloc(p->tc ? tc_weight_ws_bytes() : 0);
   p->total = cur;
   return 0;
 }
@@ -233,28 +242,42 @@ struct Ctx {
   const NetSpec* s; const Plan* p; char* ws; const float* params; float* buffers; float* grads;
   cudaStream_t st; float momentum, eps; int training;
   float* f(size_t off) const { return reinterpret_cast<float*>(ws + off); }
+  __nv_bfloat16* h(size_t off) const { return reinterpret_cast<__nv_bfloat16*>(ws + off); }
+  TcPlanes planes(const PlaneBufs& b) const { return TcPlanes{h(b.hi), h(b.lo)}; }
 };
 
-// one conv (forward): packs the weights, then runs the contraction chosen by `precision`
-static int conv_forward(const Ctx& c, const ConvSpec& cs, const float* in, float* out, int N, int Hin, int Win, int Hout, int Wout,
-                        int cin_eff) {
-  const float* w = c.params + cs.w_off;
-  const double fl = 2.0 * N * Hout * Wout * (double)cs.cout * cs.k * cs.k * cs.cin;
-  if (c.p->precision != DDN_PRECISION_FP32_SIMT && tc_conv_supported(cs.cin, cs.cout, cs.k, cs.stride, cs.pad, cs.dil, Hin, Win)) {
-    return tc_conv_forward(in, w, out, N, Hin, Win, cs.cin, cs.cout, cs.k, cs.pad, cs.dil, c.p->precision,
-                           c.ws + c.p->tc, c.p->tc_bytes, c.st);
-  }
-  ConvGeom g;
-  DDN_TRY(conv_geom_init(&g, N, Hin, Win, cin_eff, Hout, Wout, cs.cout, cs.k, cs.k, cs.stride, 1, cs.pad, cs.dil));
-  DDN_TRY(launch_pack_weights(w, c.f(c.p->wpack), cs.cout, cs.cin, cin_eff, cs.k, cs.k, 0, c.st));
-  ProfScope ps(PROF_CONV_FWD_SIMT, fl, c.st);
-  return launch_conv_gather_f32(in, c.f(c.p->wpack), nullptr, out, g, c.st);
+static bool conv_on_tc(const Ctx& c, const ConvSpec& cs, int Hin, int Win) {
+  return c.p->tc && tc_conv_supported(cs.cin, cs.cout, cs.k, cs.stride, cs.pad, cs.dil, Hin, Win);
 }
 
-static int bn_forward_stats(const Ctx& c, const BnSpec& b, const float* raw, int64_t M, float* mean, float* invstd) {
+// one conv (forward) + the statistics of the BatchNorm that follows it.
+// Tensor-core convs read the bf16 planes of their input and produce the BN partial sums in their epilogue; the
+// fp32 SIMT convs read the fp32 tensor and the column sums come from a separate pass.
+static int conv_bn_forward(const Ctx& c, const ConvSpec& cs, const BnSpec& bs, const float* in, const PlaneBufs& in_p,
+                           const ConvBufs& cb, int N, int cin_eff) {
+  const float* w = c.params + cs.w_off;
+  float* raw = c.f(cb.raw);
+  const int64_t M = (int64_t)N * cb.Hout * cb.Wout;
+  float* rm = c.buffers + bs.rm_off; float* rv = c.buffers + bs.rv_off;
+  if (conv_on_tc(c, cs, cb.Hin, cb.Win)) {
+    float* partial = c.training ? c.f(c.p->partial) : nullptr;
+    DDN_TRY(tc_conv_planes(c.planes(in_p), w, raw, nullptr, partial, N, cb.Hin, cb.Win, cs.cin, cs.cout, cs.k, cs.dil, 0,
+                           c.p->precision, c.ws + c.p->wws, tc_weight_ws_bytes(), c.st));
+    if (c.training)
+      return launch_bn_stats_finalize(partial, tc_bn_partial_blocks(N, cb.Hin, cb.Win), M, bs.C, c.f(cb.mean), c.f(cb.invstd),
+                                      rm, rv, c.momentum, c.eps, c.st);
+    return launch_bn_eval_stats(rm, rv, bs.C, c.eps, c.f(cb.mean), c.f(cb.invstd), c.st);
+  }
+  ConvGeom g;
+  DDN_TRY(conv_geom_init(&g, N, cb.Hin, cb.Win, cin_eff, cb.Hout, cb.Wout, cs.cout, cs.k, cs.k, cs.stride, 1, cs.pad, cs.dil));
+  DDN_TRY(launch_pack_weights(w, c.f(c.p->wpack), cs.cout, cs.cin, cin_eff, cs.k, cs.k, 0, c.st));
+  {
+    ProfScope ps(PROF_CONV_FWD_SIMT, 2.0 * M * (double)cs.cout * cs.k * cs.k * cs.cin, c.st);
+    DDN_TRY(launch_conv_gather_f32(in, c.f(c.p->wpack), nullptr, raw, g, c.st));
+  }
   if (c.training)
-    return launch_bn_stats(raw, M, b.C, c.f(c.p->partial), mean, invstd, c.buffers + b.rm_off, c.buffers + b.rv_off, c.momentum, c.eps, c.st);
-  return launch_bn_eval_stats(c.buffers + b.rm_off, c.buffers + b.rv_off, b.C, c.eps, mean, invstd, c.st);
+    return launch_bn_stats(raw, M, bs.C, c.f(c.p->partial), c.f(cb.mean), c.f(cb.invstd), rm, rv, c.momentum, c.eps, c.st);
+  return launch_bn_eval_stats(rm, rv, bs.C, c.eps, c.f(cb.mean), c.f(cb.invstd), c.st);
 }
 
 static int net_forward(const Ctx& c, const float* x, float* y) {
@@ -262,32 +285,35 @@ static int net_forward(const Ctx& c, const float* x, float* y) {
   const int B = p.B;
   // stem: conv1 7x7/2 -> bn1 -> relu -> maxpool 3x3/2          (resnet.py:232-235)
   DDN_TRY(launch_nchw_to_nhwc4(x, c.f(p.x4), B, p.H, p.W, c.st));
-  DDN_TRY(conv_forward(c, s.stem, c.f(p.x4), c.f(p.stem_raw), B, p.H, p.W, p.H1, p.W1, 4));
-  DDN_TRY(bn_forward_stats(c, s.stem_bn, c.f(p.stem_raw), (int64_t)B * p.H1 * p.W1, c.f(p.stem_mean), c.f(p.stem_invstd)));
+  ConvBufs stem_cb{p.stem_raw, p.stem_mean, p.stem_invstd, p.H, p.W, p.H1, p.W1};
+  DDN_TRY(conv_bn_forward(c, s.stem, s.stem_bn, c.f(p.x4), PlaneBufs{0, 0}, stem_cb, B, 4));
   DDN_TRY(launch_stem_bn_relu_pool(c.f(p.stem_raw), c.f(p.stem_mean), c.f(p.stem_invstd), c.params + s.stem_bn.g_off,
                                    c.params + s.stem_bn.b_off, c.f(p.pool_out), reinterpret_cast<uint8_t*>(c.ws + p.argmax),
+                                   p.tc ? c.h(p.pool_p.hi) : nullptr, p.tc ? c.h(p.pool_p.lo) : nullptr,
                                    B, p.H1, p.W1, 64, c.st));
   const float* cur = c.f(p.pool_out);
+  PlaneBufs cur_p = p.pool_p;
+  const bool want_lo = p.precision == DDN_PRECISION_BF16X3;
   for (size_t i = 0; i < s.blocks.size(); ++i) {        // BasicBlock.forward, resnet.py:53-69
     const BlockSpec& b = s.blocks[i]; const BlockBufs& bb = p.blk[i];
     int64_t M1 = (int64_t)B * bb.c1.Hout * bb.c1.Wout;
-    DDN_TRY(conv_forward(c, b.c1, cur, c.f(bb.c1.raw), B, bb.c1.Hin, bb.c1.Win, bb.c1.Hout, bb.c1.Wout, b.c1.cin));
-    DDN_TRY(bn_forward_stats(c, b.b1, c.f(bb.c1.raw), M1, c.f(bb.c1.mean), c.f(bb.c1.invstd)));
+    DDN_TRY(conv_bn_forward(c, b.c1, b.b1, cur, cur_p, bb.c1, B, b.c1.cin));
     BnApplyArgs a1 = {c.f(bb.c1.raw), c.f(bb.c1.mean), c.f(bb.c1.invstd), c.params + b.b1.g_off, c.params + b.b1.b_off,
-                      nullptr, nullptr, nullptr, nullptr, nullptr, c.f(bb.act1), M1, b.b1.C, 1};
+                      nullptr, nullptr, nullptr, nullptr, nullptr, c.f(bb.act1), M1, b.b1.C, 1,
+                      p.tc ? c.h(bb.act1_p.hi) : nullptr, (p.tc && want_lo) ? c.h(bb.act1_p.lo) : nullptr};
     DDN_TRY(launch_bn_apply(a1, c.st));
-    DDN_TRY(conv_forward(c, b.c2, c.f(bb.act1), c.f(bb.c2.raw), B, bb.c2.Hin, bb.c2.Win, bb.c2.Hout, bb.c2.Wout, b.c2.cin));
-    DDN_TRY(bn_forward_stats(c, b.b2, c.f(bb.c2.raw), M1, c.f(bb.c2.mean), c.f(bb.c2.invstd)));
+    DDN_TRY(conv_bn_forward(c, b.c2, b.b2, c.f(bb.act1), bb.act1_p, bb.c2, B, b.c2.cin));
     BnApplyArgs a2 = {c.f(bb.c2.raw), c.f(bb.c2.mean), c.f(bb.c2.invstd), c.params + b.b2.g_off, c.params + b.b2.b_off,
-                      cur, nullptr, nullptr, nullptr, nullptr, c.f(bb.out), M1, b.b2.C, 1};
+                      cur, nullptr, nullptr, nullptr, nullptr, c.f(bb.out), M1, b.b2.C, 1,
+                      p.tc ? c.h(bb.out_p.hi) : nullptr, (p.tc && want_lo) ? c.h(bb.out_p.lo) : nullptr};
     if (b.has_ds) {
-      DDN_TRY(conv_forward(c, b.ds, cur, c.f(bb.ds.raw), B, bb.ds.Hin, bb.ds.Win, bb.ds.Hout, bb.ds.Wout, b.ds.cin));
-      DDN_TRY(bn_forward_stats(c, b.bd, c.f(bb.ds.raw), M1, c.f(bb.ds.mean), c.f(bb.ds.invstd)));
+      DDN_TRY(conv_bn_forward(c, b.ds, b.bd, cur, cur_p, bb.ds, B, b.ds.cin));
       a2.r = c.f(bb.ds.raw); a2.rmean = c.f(bb.ds.mean); a2.rinvstd = c.f(bb.ds.invstd);
       a2.rgamma = c.params + b.bd.g_off; a2.rbeta = c.params + b.bd.b_off;
     }
     DDN_TRY(launch_bn_apply(a2, c.st));
     cur = c.f(bb.out);
+    cur_p = bb.out_p;
   }
   // fc (1x1 conv + bias) and the bilinear upsample back to the input size      (resnet.py:263, resnet_dilated.py:320)
   const int h8 = p.H / 8, w8 = p.W / 8;
@@ -296,16 +322,22 @@ static int net_forward(const Ctx& c, const float* x, float* y) {
   return 0;
 }
 
-// conv backward: dw -> grads (always), dx -> `dx` (+ addend) when dx != nullptr
-static int conv_backward(const Ctx& c, const ConvSpec& cs, const float* in, const float* dy, float* dx, const float* addend,
-                         int N, int Hin, int Win, int Hout, int Wout, int cin_eff) {
+// conv backward: dw -> grads (always), dx -> `dx` (+ addend) when dx != nullptr.
+// Tensor-core convs take the saved bf16 planes of their input and the planes of dY (p.grad_p, written by the BN
+// backward that precedes this call); the fp32 SIMT convs take the fp32 tensors.
+static int conv_backward(const Ctx& c, const ConvSpec& cs, const float* in, const PlaneBufs& in_p, const float* dy, float* dx,
+                         const float* addend, int N, int Hin, int Win, int Hout, int Wout, int cin_eff) {
   const Plan& p = *c.p;
   const float* w = c.params + cs.w_off;
   float* dw = c.grads + cs.w_off;
   const double fl = 2.0 * N * Hout * Wout * (double)cs.cout * cs.k * cs.k * cs.cin;
-  if (p.precision != DDN_PRECISION_FP32_SIMT && tc_conv_supported(cs.cin, cs.cout, cs.k, cs.stride, cs.pad, cs.dil, Hin, Win)) {
-    return tc_conv_backward(in, w, dy, dx, addend, dw, N, Hin, Win, cs.cin, cs.cout, cs.k, cs.pad, cs.dil, p.precision,
-                            c.ws + p.tc, p.tc_bytes, c.f(p.dwp), c.st);
+  if (conv_on_tc(c, cs, Hin, Win)) {
+    DDN_TRY(tc_wgrad_planes(c.planes(in_p), c.planes(p.grad_p), dw, N, Hin, Win, cs.cin, cs.cout, cs.k, cs.dil, p.precision,
+                            c.f(p.dwp), c.st));
+    if (dx)
+      DDN_TRY(tc_conv_planes(c.planes(p.grad_p), w, dx, addend, nullptr, N, Hin, Win, cs.cin, cs.cout, cs.k, cs.dil, 1,
+                             p.precision, c.ws + p.wws, tc_weight_ws_bytes(), c.st));
+    return 0;
   }
   ConvGeom g;
   DDN_TRY(conv_geom_init(&g, N, Hin, Win, cin_eff, Hout, Wout, cs.cout, cs.k, cs.k, cs.stride, 1, cs.pad, cs.dil));
@@ -326,6 +358,18 @@ static int conv_backward(const Ctx& c, const ConvSpec& cs, const float* in, cons
   return 0;
 }
 
+// BN backward whose dx feeds `cs`'s backward: planes for a tensor-core conv, fp32 for a SIMT conv
+static int bn_backward_for(const Ctx& c, BnBwdArgs a, const ConvSpec& cs, int Hin, int Win, float* dx_f32) {
+  if (conv_on_tc(c, cs, Hin, Win)) {
+    a.dx = nullptr;
+    a.dx_hi = c.h(c.p->grad_p.hi);
+    a.dx_lo = c.p->precision == DDN_PRECISION_BF16X3 ? c.h(c.p->grad_p.lo) : nullptr;
+  } else {
+    a.dx = dx_f32; a.dx_hi = nullptr; a.dx_lo = nullptr;
+  }
+  return launch_bn_backward(a, c.st);
+}
+
 static int net_backward(const Ctx& c, const float* dy) {
   const NetSpec& s = *c.s; const Plan& p = *c.p;
   const int B = p.B, h8 = p.H / 8, w8 = p.W / 8;
@@ -338,30 +382,33 @@ static int net_backward(const Ctx& c, const float* dy) {
   for (int i = (int)s.blocks.size() - 1; i >= 0; --i) {
     const BlockSpec& b = s.blocks[i]; const BlockBufs& bb = p.blk[i];
     const float* xin = i == 0 ? c.f(p.pool_out) : c.f(p.blk[i - 1].out);
+    const PlaneBufs xin_p = i == 0 ? p.pool_p : p.blk[i - 1].out_p;
     int64_t M1 = (int64_t)B * bb.c1.Hout * bb.c1.Wout;
     int t1 = (cur + 1) & 3, t2 = (cur + 2) & 3, t3 = (cur + 3) & 3;
-    // out = relu(bn2(raw2) + residual):  g = dOut*(out>0) -> S[t2];  d raw2 -> S[t1]
+    // out = relu(bn2(raw2) + residual):  g = dOut*(out>0) -> S[t2];  d raw2 -> planes (tensor core) or S[t1] (fp32)
     BnBwdArgs k2 = {S[cur], c.f(bb.out), c.f(bb.c2.raw), c.f(bb.c2.mean), c.f(bb.c2.invstd), c.params + b.b2.g_off,
-                    S[t1], c.grads + b.b2.g_off, c.grads + b.b2.b_off, S[t2], c.f(p.partial), M1, b.b2.C, 1, 1};
-    DDN_TRY(launch_bn_backward(k2, c.st));
+                    nullptr, c.grads + b.b2.g_off, c.grads + b.b2.b_off, S[t2], c.f(p.partial), M1, b.b2.C, 1, 1, nullptr, nullptr};
+    DDN_TRY(bn_backward_for(c, k2, b.c2, bb.c2.Hin, bb.c2.Win, S[t1]));
     // conv2: dW, d act1 -> S[t3]
-    DDN_TRY(conv_backward(c, b.c2, c.f(bb.act1), S[t1], S[t3], nullptr, B, bb.c2.Hin, bb.c2.Win, bb.c2.Hout, bb.c2.Wout, b.c2.cin));
-    // act1 = relu(bn1(raw1)): d raw1 -> S[t1]
+    DDN_TRY(conv_backward(c, b.c2, c.f(bb.act1), bb.act1_p, S[t1], S[t3], nullptr, B, bb.c2.Hin, bb.c2.Win, bb.c2.Hout, bb.c2.Wout, b.c2.cin));
+    // act1 = relu(bn1(raw1)): d raw1
     BnBwdArgs k1 = {S[t3], c.f(bb.act1), c.f(bb.c1.raw), c.f(bb.c1.mean), c.f(bb.c1.invstd), c.params + b.b1.g_off,
-                    S[t1], c.grads + b.b1.g_off, c.grads + b.b1.b_off, nullptr, c.f(p.partial), M1, b.b1.C, 1, 1};
-    DDN_TRY(launch_bn_backward(k1, c.st));
-    const bool need_dx = true;   // pool_out's gradient feeds the stem's BN/conv weight gradients
+                    nullptr, c.grads + b.b1.g_off, c.grads + b.b1.b_off, nullptr, c.f(p.partial), M1, b.b1.C, 1, 1, nullptr, nullptr};
     if (!b.has_ds) {
+      DDN_TRY(bn_backward_for(c, k1, b.c1, bb.c1.Hin, bb.c1.Win, S[t1]));
       // dX = dgrad(conv1) + g
-      DDN_TRY(conv_backward(c, b.c1, xin, S[t1], need_dx ? S[t3] : nullptr, S[t2], B, bb.c1.Hin, bb.c1.Win, bb.c1.Hout, bb.c1.Wout, b.c1.cin));
+      DDN_TRY(conv_backward(c, b.c1, xin, xin_p, S[t1], S[t3], S[t2], B, bb.c1.Hin, bb.c1.Win, bb.c1.Hout, bb.c1.Wout, b.c1.cin));
       cur = t3;
     } else {
-      // residual branch: bn_d(raw_d): d raw_d -> S[t3]; ds conv: dW, dX_ds -> S[cur]; then dX = dgrad(conv1) + dX_ds -> S[t2]
+      // residual branch first (its dY planes are consumed before conv1's overwrite them):
+      // bn_d(raw_d): d raw_d; ds conv: dW, dX_ds -> S[cur]
       BnBwdArgs kd = {S[t2], nullptr, c.f(bb.ds.raw), c.f(bb.ds.mean), c.f(bb.ds.invstd), c.params + b.bd.g_off,
-                      S[t3], c.grads + b.bd.g_off, c.grads + b.bd.b_off, nullptr, c.f(p.partial), M1, b.bd.C, 0, 1};
-      DDN_TRY(launch_bn_backward(kd, c.st));
-      DDN_TRY(conv_backward(c, b.ds, xin, S[t3], S[cur], nullptr, B, bb.ds.Hin, bb.ds.Win, bb.ds.Hout, bb.ds.Wout, b.ds.cin));
-      DDN_TRY(conv_backward(c, b.c1, xin, S[t1], S[t2], S[cur], B, bb.c1.Hin, bb.c1.Win, bb.c1.Hout, bb.c1.Wout, b.c1.cin));
+                      nullptr, c.grads + b.bd.g_off, c.grads + b.bd.b_off, nullptr, c.f(p.partial), M1, b.bd.C, 0, 1, nullptr, nullptr};
+      DDN_TRY(bn_backward_for(c, kd, b.ds, bb.ds.Hin, bb.ds.Win, S[t1]));
+      DDN_TRY(conv_backward(c, b.ds, xin, xin_p, S[t1], S[cur], nullptr, B, bb.ds.Hin, bb.ds.Win, bb.ds.Hout, bb.ds.Wout, b.ds.cin));
+      // main branch: d raw1, then dX = dgrad(conv1) + dX_ds -> S[t2]
+      DDN_TRY(bn_backward_for(c, k1, b.c1, bb.c1.Hin, bb.c1.Win, S[t1]));
+      DDN_TRY(conv_backward(c, b.c1, xin, xin_p, S[t1], S[t2], S[cur], B, bb.c1.Hin, bb.c1.Win, bb.c1.Hout, bb.c1.Wout, b.c1.cin));
       cur = t2;
     }
   }
@@ -372,9 +419,9 @@ static int net_backward(const Ctx& c, const float* dy) {
                                          c.params + s.stem_bn.b_off, S[t1], B, p.H1, p.W1, 64, c.st));
   BnBwdArgs ks = {S[t1], nullptr, c.f(p.stem_raw), c.f(p.stem_mean), c.f(p.stem_invstd), c.params + s.stem_bn.g_off,
                   S[t2], c.grads + s.stem_bn.g_off, c.grads + s.stem_bn.b_off, nullptr, c.f(p.partial),
-                  (int64_t)B * p.H1 * p.W1, 64, 0, 1};
+                  (int64_t)B * p.H1 * p.W1, 64, 0, 1, nullptr, nullptr};
   DDN_TRY(launch_bn_backward(ks, c.st));
-  DDN_TRY(conv_backward(c, s.stem, c.f(p.x4), S[t2], nullptr, nullptr, B, p.H, p.W, p.H1, p.W1, 4));
+  DDN_TRY(conv_backward(c, s.stem, c.f(p.x4), PlaneBufs{0, 0}, S[t2], nullptr, nullptr, B, p.H, p.W, p.H1, p.W1, 4));
   return 0;
 }
 
