@@ -88,24 +88,31 @@ bn_colsum_kernel(const float* __restrict__ x, const float* __restrict__ dy, cons
   }
 }
 
-// Column sums of the per-block partials in fp64: 32 channels x 8 slices per block (coalesced 128-byte rows),
-// so the serial chain per thread is nblk/8 instead of nblk.
+// Column sums of the per-block partials in fp64.  Block = 8 channels (one 32-byte sector per partial row) x 32 slices;
+// every thread walks nblk/32 rows with 4 independent loads in flight, so the chain is a few iterations long even for
+// ~1200 partial rows (the previous 8-slice version spent 40-50 us per call in load latency on 2-16 CTAs).
 __device__ __forceinline__ void reduce_partials(const float* __restrict__ partial, int nblk, int C, int c, int slice,
                                                 double& s, double& ss) {
-  s = 0; ss = 0;
+  double s0 = 0, s1 = 0, q0 = 0, q1 = 0;
   if (c < C) {
-    for (int b = slice; b < nblk; b += 8) {
-      s += (double)__ldg(partial + (int64_t)b * C + c);
-      ss += (double)__ldg(partial + ((int64_t)nblk + b) * C + c);
+    const float* ps = partial + c;
+    const float* pq = partial + (int64_t)nblk * C + c;
+    int b = slice;
+    for (; b + 32 < nblk; b += 64) {
+      float a0 = __ldg(ps + (int64_t)b * C), a1 = __ldg(ps + (int64_t)(b + 32) * C);
+      float b0 = __ldg(pq + (int64_t)b * C), b1 = __ldg(pq + (int64_t)(b + 32) * C);
+      s0 += (double)a0; s1 += (double)a1; q0 += (double)b0; q1 += (double)b1;
     }
+    if (b < nblk) { s0 += (double)__ldg(ps + (int64_t)b * C); q0 += (double)__ldg(pq + (int64_t)b * C); }
   }
-  __shared__ double sh[2][8][32];
-  const int lane = threadIdx.x & 31;
-  sh[0][slice][lane] = s; sh[1][slice][lane] = ss;
+  s = s0 + s1; ss = q0 + q1;
+  __shared__ double sh[2][32][8];
+  const int ch = threadIdx.x & 7;
+  sh[0][slice][ch] = s; sh[1][slice][ch] = ss;
   __syncthreads();
   if (slice == 0) {
-#pragma unroll
-    for (int k = 1; k < 8; ++k) { s += sh[0][k][lane]; ss += sh[1][k][lane]; }
+#pragma unroll 8
+    for (int k = 1; k < 32; ++k) { s += sh[0][k][ch]; ss += sh[1][k][ch]; }
   }
 }
 
@@ -114,7 +121,7 @@ bn_stats_finalize_kernel(const float* __restrict__ partial, int nblk, int64_t M,
                          float* __restrict__ mean, float* __restrict__ invstd,
                          float* __restrict__ running_mean, float* __restrict__ running_var,
                          float momentum, float eps) {
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31), slice = threadIdx.x >> 5;
+  const int c = blockIdx.x * 8 + (threadIdx.x & 7), slice = threadIdx.x >> 3;
   double s, ss;
   reduce_partials(partial, nblk, C, c, slice, s, ss);
   if (slice != 0 || c >= C) return;
@@ -173,7 +180,7 @@ bn_apply_kernel(BnApplyArgs a) {
 __global__ void __launch_bounds__(256)
 bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C,
                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31), slice = threadIdx.x >> 5;
+  const int c = blockIdx.x * 8 + (threadIdx.x & 7), slice = threadIdx.x >> 3;
   double s, ss;
   reduce_partials(partial, nblk, C, c, slice, s, ss);
   if (slice != 0 || c >= C) return;
@@ -315,14 +322,14 @@ int launch_bn_stats(const float* x, int64_t M, int C, float* partial, float* mea
   int nblk = bn_partial_blocks(M, C);
   DDN_LAUNCH(bn_colsum_kernel<0>, nblk, BN_THREADS, 0, st, x, nullptr, nullptr, nullptr, nullptr, M, C,
              bn_rows_per_block(M, C), 0, partial);
-  DDN_LAUNCH(bn_stats_finalize_kernel, (int)ceil_div(C, 32), 256, 0, st, partial, nblk, M, C, mean, invstd,
+  DDN_LAUNCH(bn_stats_finalize_kernel, (int)ceil_div(C, 8), 256, 0, st, partial, nblk, M, C, mean, invstd,
              running_mean, running_var, momentum, eps);
   return 0;
 }
 
 int launch_bn_stats_finalize(const float* partial, int nblk, int64_t M, int C, float* mean, float* invstd,
                              float* running_mean, float* running_var, float momentum, float eps, cudaStream_t st) {
-  DDN_LAUNCH(bn_stats_finalize_kernel, (int)ceil_div(C, 32), 256, 0, st, partial, nblk, M, C, mean, invstd,
+  DDN_LAUNCH(bn_stats_finalize_kernel, (int)ceil_div(C, 8), 256, 0, st, partial, nblk, M, C, mean, invstd,
              running_mean, running_var, momentum, eps);
   return 0;
 }
@@ -343,7 +350,7 @@ int launch_bn_backward(const BnBwdArgs& a, cudaStream_t st) {
   int nblk = bn_partial_blocks(a.M, a.C);
   DDN_LAUNCH(bn_colsum_kernel<1>, nblk, BN_THREADS, 0, st, a.x, a.dy, a.y, a.mean, a.invstd, a.M, a.C,
              bn_rows_per_block(a.M, a.C), a.relu, a.partial);
-  DDN_LAUNCH(bn_bwd_finalize_kernel, (int)ceil_div(a.C, 32), 256, 0, st, a.partial, nblk, a.C, a.dgamma, a.dbeta);
+  DDN_LAUNCH(bn_bwd_finalize_kernel, (int)ceil_div(a.C, 8), 256, 0, st, a.partial, nblk, a.C, a.dgamma, a.dbeta);
   DDN_LAUNCH(bn_bwd_apply_kernel, ew_blocks(a.M * (a.C / 4)), BN_THREADS, 5 * a.C * sizeof(float), st, a);
   return 0;
 }
