@@ -128,6 +128,7 @@ struct TcConvParams {
   int N, H, W, Cin, Cout;
   int taps_w;            // 1 or 3 (k x k filter)
   int dil;
+  int stride;            // 1, or 2 (forward only: the A tensor map then samples every other input pixel)
   int tiles_h, tiles_w;
   float* bn_partial;     // optional [2][gridDim.x][Cout]: per-tile column sums / sums of squares of the conv output
 };
@@ -202,7 +203,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
         const int tap = kb / cin_chunks, cc = kb - tap * cin_chunks;
         const int r = tap / p.taps_w, sx = tap - r * p.taps_w;
-        const int hh = h0 + (r - half) * p.dil, ww = w0 + (sx - half) * p.dil;
+        const int hh = h0 * p.stride + (r - half) * p.dil, ww = w0 * p.stride + (sx - half) * p.dil;
         uint8_t* st = smem + (size_t)s * STAGE_BYTES;
         const uint32_t bar = smem_u32(&full_bar[s]);
         mbar_expect_tx(bar, STAGE_BYTES);
@@ -314,8 +315,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 struct TcWgradParams {
   float* dwp;            // [taps][Cout][Cin] fp32, zero-filled by the caller
   int N, H, W, Cin, Cout;
-  int taps_w, dil;
-  int tiles_h, tiles_w;  // 4x16 pixel patches per image
+  int taps_w, dil, stride;
+  int tiles_h, tiles_w;  // 4x16 (output-)pixel patches per image
   int kb_per_split;      // pixel patches per CTA (grid.z splits)
 };
 
@@ -401,7 +402,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_const
             mbar_wait(smem_u32(&empty_b[sb]), ((j / SB) & 1) ^ 1);
             const int r = (T == 1) ? half : tap_row;            // 1x1: the only tap; 3x3: this CTA's filter row
             const int sx = (T == 1) ? half : t;
-            const int hh = h0 + (r - half) * p.dil, ww = w0 + (sx - half) * p.dil;
+            const int hh = h0 * p.stride + (r - half) * p.dil, ww = w0 * p.stride + (sx - half) * p.dil;
             const uint32_t bar_b = smem_u32(&full_b[sb]);
             mbar_expect_tx(bar_b, B_STAGE);
 #pragma unroll
@@ -530,6 +531,90 @@ __global__ void pack_weights_tc_kernel(const float* __restrict__ w, __nv_bfloat1
   }
 }
 
+
+// dY fp32 [N,Ho,Wo,C] -> zero-inserted bf16 planes [N,2Ho,2Wo,C]: value at (2ho,2wo), zeros at the other three positions.
+// The data gradient of a stride-2 convolution is then an ordinary stride-1 convolution over these planes.
+__global__ void upsample_zero_split_kernel(const float* __restrict__ dy, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                           int N, int Ho, int Wo, int C, int want_lo) {
+  const int q = C >> 2;
+  const int64_t total = (int64_t)N * Ho * Wo * q;
+  const uint2 z = make_uint2(0u, 0u);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c4 = (int)(i % q); int64_t t = i / q;
+    int wo = (int)(t % Wo); t /= Wo;
+    int ho = (int)(t % Ho); int n = (int)(t / Ho);
+    float4 v = __ldg(reinterpret_cast<const float4*>(dy) + i);
+    __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z), h3 = __float2bfloat16_rn(v.w);
+    __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
+    uint2 hv; hv.x = *reinterpret_cast<uint32_t*>(&a); hv.y = *reinterpret_cast<uint32_t*>(&b);
+    uint2 lv = z;
+    if (want_lo) {
+      __nv_bfloat162 c = __halves2bfloat162(__float2bfloat16_rn(v.x - __bfloat162float(h0)), __float2bfloat16_rn(v.y - __bfloat162float(h1)));
+      __nv_bfloat162 d = __halves2bfloat162(__float2bfloat16_rn(v.z - __bfloat162float(h2)), __float2bfloat16_rn(v.w - __bfloat162float(h3)));
+      lv.x = *reinterpret_cast<uint32_t*>(&c); lv.y = *reinterpret_cast<uint32_t*>(&d);
+    }
+    const int64_t W2 = 2 * Wo;
+    const int64_t base = (((int64_t)n * 2 * Ho + 2 * ho) * W2 + 2 * wo) * q + c4;
+    uint2* H = reinterpret_cast<uint2*>(hi); uint2* L = reinterpret_cast<uint2*>(lo);
+    H[base] = hv; H[base + q] = z; H[base + W2 * q] = z; H[base + W2 * q + q] = z;
+    if (want_lo) { L[base] = lv; L[base + q] = z; L[base + W2 * q] = z; L[base + W2 * q + q] = z; }
+  }
+}
+
+// Stem: x fp32 NCHW [N,3,H,W] -> 7x7/2 patch planes [N,H1,W1,192] bf16 (k = (r*7+s)*3 + c for k < 147, zero above), so
+// that conv1 becomes a GEMM with K = 192 on the tensor cores.
+__global__ void stem_patch_split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                        int N, int H, int W, int H1, int W1, int want_lo) {
+  const int64_t total = (int64_t)N * H1 * W1 * 48;      // 48 quads of 4 k-values per output pixel
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int kq = (int)(i % 48); int64_t t = i / 48;
+    int wo = (int)(t % W1); t /= W1;
+    int ho = (int)(t % H1); int n = (int)(t / H1);
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int k = kq * 4 + j;
+      float val = 0.f;
+      if (k < 147) {
+        int c = k % 3, rs = k / 3, r = rs / 7, s = rs - r * 7;
+        int h = 2 * ho - 3 + r, w = 2 * wo - 3 + s;
+        if (h >= 0 && h < H && w >= 0 && w < W) val = __ldg(x + (((int64_t)n * 3 + c) * H + h) * W + w);
+      }
+      v[j] = val;
+    }
+    __nv_bfloat16 h0 = __float2bfloat16_rn(v[0]), h1 = __float2bfloat16_rn(v[1]), h2 = __float2bfloat16_rn(v[2]), h3 = __float2bfloat16_rn(v[3]);
+    __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
+    uint2 hv; hv.x = *reinterpret_cast<uint32_t*>(&a); hv.y = *reinterpret_cast<uint32_t*>(&b);
+    reinterpret_cast<uint2*>(hi)[i] = hv;
+    if (want_lo) {
+      __nv_bfloat162 c = __halves2bfloat162(__float2bfloat16_rn(v[0] - __bfloat162float(h0)), __float2bfloat16_rn(v[1] - __bfloat162float(h1)));
+      __nv_bfloat162 d = __halves2bfloat162(__float2bfloat16_rn(v[2] - __bfloat162float(h2)), __float2bfloat16_rn(v[3] - __bfloat162float(h3)));
+      uint2 lv; lv.x = *reinterpret_cast<uint32_t*>(&c); lv.y = *reinterpret_cast<uint32_t*>(&d);
+      reinterpret_cast<uint2*>(lo)[i] = lv;
+    }
+  }
+}
+
+// conv1.weight [64][3][7][7] fp32 -> B[co][k] bf16 hi/lo with k = (r*7+s)*3 + c, zero for k in [147,192)
+__global__ void stem_pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int want_lo) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * 192) return;
+  int k = i % 192, co = i / 192;
+  float v = 0.f;
+  if (k < 147) { int c = k % 3, rs = k / 3; v = w[(co * 3 + c) * 49 + rs]; }
+  __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi[i] = h;
+  if (want_lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+// dW'[co][192] -> conv1.weight gradient [64][3][7][7]
+__global__ void stem_unpack_wgrad_kernel(const float* __restrict__ dwk, float* __restrict__ dw) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * 147) return;
+  int rs = i % 49, c = (i / 49) % 3, co = i / 147;
+  dw[i] = dwk[co * 192 + rs * 3 + c];
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -549,13 +634,15 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int box_h = TC_TH) {
+// `sample` = traversal stride in W and H (elementStrides): a box then spans box*sample input pixels and delivers every
+// sample-th one, which is how a stride-2 convolution reads its input without a strided copy.
+static int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int box_h = TC_TH, int sample = 1) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)"); return DDN_EUNSUPPORTED; }
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {TC_BLOCK_K, TC_TW, (cuuint32_t)box_h, 1};
-  cuuint32_t es[4] = {1, 1, 1, 1};
+  cuuint32_t box[4] = {TC_BLOCK_K, (cuuint32_t)(TC_TW * sample), (cuuint32_t)(box_h * sample), 1};
+  cuuint32_t es[4] = {1, (cuuint32_t)sample, (cuuint32_t)sample, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -596,21 +683,23 @@ static int launch_wgrad_tc(const CUtensorMap& dy_hi, const CUtensorMap& dy_lo, c
   return 0;
 }
 
-// dw[Cout][Cin][k][k] (overwritten) from the bf16 planes of x [N,H,W,Cin] and dy [N,H,W,Cout].
-int tc_wgrad_planes(TcPlanes x, TcPlanes dy, float* dw, int N, int H, int W, int Cin, int Cout, int k, int dil,
+// dw[Cout][Cin][k][k] (overwritten) from the bf16 planes of x [N,H,W,Cin] and dy [N,Ho,Wo,Cout] (Ho = H/stride).
+// `dw_packed` != nullptr: leave the result as [taps][... see unpack] -> written as dw'[Cout][Cin*taps] (stem path).
+int tc_wgrad_planes(TcPlanes x, TcPlanes dy, float* dw, int N, int H, int W, int Cin, int Cout, int k, int stride, int dil,
                     int precision, float* dwp, cudaStream_t st) {
   const int want_lo = precision == DDN_PRECISION_BF16X3;
   const int taps = k * k;
+  const int Ho = H / stride, Wo = W / stride;
   DDN_TRY(launch_fill_zero(dwp, sizeof(float) * (size_t)taps * Cout * Cin, st));
   const int bn = Cin % 128 == 0 ? 128 : 64;
   CUtensorMap m_dy_hi, m_dy_lo, m_x_hi, m_x_lo;
-  DDN_TRY(make_act_map(&m_dy_hi, dy.hi, N, H, W, Cout, 4));
-  DDN_TRY(make_act_map(&m_dy_lo, want_lo ? dy.lo : dy.hi, N, H, W, Cout, 4));
-  DDN_TRY(make_act_map(&m_x_hi, x.hi, N, H, W, Cin, 4));
-  DDN_TRY(make_act_map(&m_x_lo, want_lo ? x.lo : x.hi, N, H, W, Cin, 4));
+  DDN_TRY(make_act_map(&m_dy_hi, dy.hi, N, Ho, Wo, Cout, 4));
+  DDN_TRY(make_act_map(&m_dy_lo, want_lo ? dy.lo : dy.hi, N, Ho, Wo, Cout, 4));
+  DDN_TRY(make_act_map(&m_x_hi, x.hi, N, H, W, Cin, 4, stride));
+  DDN_TRY(make_act_map(&m_x_lo, want_lo ? x.lo : x.hi, N, H, W, Cin, 4, stride));
   TcWgradParams p;
-  p.dwp = dwp; p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.taps_w = k; p.dil = dil;
-  p.tiles_h = (int)ceil_div(H, 4); p.tiles_w = (int)ceil_div(W, 16);
+  p.dwp = dwp; p.N = N; p.H = Ho; p.W = Wo; p.Cin = Cin; p.Cout = Cout; p.taps_w = k; p.dil = dil; p.stride = stride;
+  p.tiles_h = (int)ceil_div(Ho, 4); p.tiles_w = (int)ceil_div(Wo, 16);
   const int total_kb = N * p.tiles_h * p.tiles_w;
   const int ctas_xy = (Cin / bn) * (k == 3 ? 3 : 1) * (int)ceil_div(Cout, 128);
   // split-K so that the grid is (just under) a whole number of waves: 1 CTA per SM resident, no ragged tail wave
@@ -619,7 +708,7 @@ int tc_wgrad_planes(TcPlanes x, TcPlanes dy, float* dw, int N, int H, int W, int
   int splits = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)waves * sms / ctas_xy, ceil_div(total_kb, 4)));
   p.kb_per_split = (int)ceil_div(total_kb, splits);
   splits = (int)ceil_div(total_kb, p.kb_per_split);
-  const double fl = 2.0 * N * H * W * (double)Cout * taps * Cin;
+  const double fl = 2.0 * N * Ho * Wo * (double)Cout * taps * Cin;
   {
     ProfScope ps(PROF_CONV_WGRAD_TC, fl, st);
 #define WG(BNV, TV)                                                                                      \
@@ -638,9 +727,11 @@ int tc_wgrad_planes(TcPlanes x, TcPlanes dy, float* dw, int N, int H, int W, int
 
 bool tc_available() { return true; }
 
+// forward / weight-gradient coverage: 3x3 (pad == dil) or 1x1 (pad 0), stride 1 -- or stride 2 with dil 1 on even sizes
 bool tc_conv_supported(int Cin, int Cout, int k, int stride, int pad, int dil, int H, int W) {
-  (void)H; (void)W;
-  if (stride != 1 || Cin % 64 || Cout % 64) return false;
+  if (Cin % 64 || Cout % 64) return false;
+  if (stride == 2) { if (dil != 1 || (H & 1) || (W & 1)) return false; }
+  else if (stride != 1) return false;
   if (k == 3) return pad == dil;
   if (k == 1) return pad == 0;
   return false;
@@ -648,13 +739,29 @@ bool tc_conv_supported(int Cin, int Cout, int k, int stride, int pad, int dil, i
 
 static const size_t kMaxWeightElems = (size_t)9 * 512 * 512;
 size_t tc_weight_ws_bytes() { return 2 * align_up(kMaxWeightElems * 2, 1024) + 2048; }
-int tc_bn_partial_blocks(int N, int H, int W) { return N * (int)ceil_div(H, TC_TH) * (int)ceil_div(W, TC_TW); }
+int tc_bn_partial_blocks(int N, int Ho, int Wo) { return N * (int)ceil_div(Ho, TC_TH) * (int)ceil_div(Wo, TC_TW); }
 
 int tc_split(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t n, int precision, cudaStream_t st) {
   DDN_CHECK_ARG(n % 4 == 0, "split: element count must be a multiple of 4");
   int64_t n4 = n / 4;
   int blocks = (int)std::min<int64_t>(ceil_div(n4, 256), (int64_t)num_sms() * 8);
   DDN_LAUNCH(split_bf16_kernel, blocks, 256, 0, st, x, hi, lo, n4, precision == DDN_PRECISION_BF16X3 ? 1 : 0);
+  return 0;
+}
+
+int tc_upsample_zero_split(const float* dy, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int Ho, int Wo, int C, int precision,
+                           cudaStream_t st) {
+  int64_t total = (int64_t)N * Ho * Wo * (C / 4);
+  int blocks = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)num_sms() * 8);
+  DDN_LAUNCH(upsample_zero_split_kernel, blocks, 256, 0, st, dy, hi, lo, N, Ho, Wo, C, precision == DDN_PRECISION_BF16X3 ? 1 : 0);
+  return 0;
+}
+
+int tc_stem_patches(const float* x_nchw, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int H, int W, int precision, cudaStream_t st) {
+  const int H1 = (H - 1) / 2 + 1, W1 = (W - 1) / 2 + 1;
+  int64_t total = (int64_t)N * H1 * W1 * 48;
+  int blocks = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)num_sms() * 16);
+  DDN_LAUNCH(stem_patch_split_kernel, blocks, 256, 0, st, x_nchw, hi, lo, N, H, W, H1, W1, precision == DDN_PRECISION_BF16X3 ? 1 : 0);
   return 0;
 }
 
@@ -675,33 +782,44 @@ static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUt
   return 0;
 }
 
-// out[N,H,W,gout] = conv(planes of in[N,H,W,gin]; weights packed on the fly) (+ addend).  dgrad = 0: forward
-// (gin = Cin, gout = Cout).  dgrad = 1: data gradient (`in` = dY planes with Cout channels, out = dX with Cin channels;
-// Cin/Cout are those of the ORIGINAL conv).  bn_partial (forward only): [2][tc_bn_partial_blocks][Cout] column sums.
-int tc_conv_planes(TcPlanes in, const float* w_oihw, float* out, const float* addend, float* bn_partial,
-                   int N, int H, int W, int Cin, int Cout, int k, int dil, int dgrad, int precision,
+// out[N,Ho,Wo,gout] = conv(planes of in[N,H,W,gin]) (+ addend).
+//   dgrad = 0: forward (gin = Cin, gout = Cout, Ho = H/stride).
+//   dgrad = 1: data gradient, stride 1 only (`in` = dY planes with Cout channels, out = dX with Cin channels; Cin/Cout are
+//              those of the ORIGINAL conv).
+//   wpk != nullptr: weights are already packed [gout][k*k*gin] bf16 hi/lo (stem path); else they are packed from w_oihw.
+//   bn_partial (forward only): [2][tc_bn_partial_blocks(N,Ho,Wo)][Cout] column sums.
+int tc_conv_planes(TcPlanes in, const float* w_oihw, const TcPlanes* wpk, float* out, const float* addend, float* bn_partial,
+                   int N, int H, int W, int Cin, int Cout, int k, int stride, int dil, int dgrad, int precision,
                    void* wws, size_t wws_bytes, cudaStream_t st) {
-  const double fl = 2.0 * N * H * W * (double)Cout * k * k * Cin;
+  DDN_CHECK_ARG(stride == 1 || !dgrad, "the strided data gradient goes through zero-inserted planes (stride 1 here)");
+  const int Ho = H / stride, Wo = W / stride;
+  const double fl = 2.0 * N * Ho * Wo * (double)Cout * k * k * Cin;
   const int gin = dgrad ? Cout : Cin, gout = dgrad ? Cin : Cout;
-  const size_t wel = (size_t)Cout * Cin * k * k;
-  const size_t w_b = align_up(kMaxWeightElems * 2, 1024);
-  DDN_CHECK_ARG(wws != nullptr && wel <= kMaxWeightElems, "tc weight staging missing or weight tensor too large");
-  char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<uintptr_t>(wws), 1024));
-  if ((size_t)(base - (char*)wws) + 2 * w_b > wws_bytes) { set_error("tcgen05 weight staging too small"); return DDN_EWORKSPACE; }
-  __nv_bfloat16* b_hi = (__nv_bfloat16*)base;
-  __nv_bfloat16* b_lo = (__nv_bfloat16*)(base + w_b);
   const int want_lo = precision == DDN_PRECISION_BF16X3;
-  int wblocks = (int)std::min<int64_t>(ceil_div((int64_t)wel, 256), 4096);
-  DDN_LAUNCH(pack_weights_tc_kernel, wblocks, 256, 0, st, w_oihw, b_hi, b_lo, Cout, Cin, k, dgrad, want_lo);
+  const __nv_bfloat16* b_hi; const __nv_bfloat16* b_lo;
+  if (wpk) {
+    b_hi = wpk->hi; b_lo = wpk->lo;
+  } else {
+    const size_t wel = (size_t)Cout * Cin * k * k;
+    const size_t w_b = align_up(kMaxWeightElems * 2, 1024);
+    DDN_CHECK_ARG(wws != nullptr && wel <= kMaxWeightElems, "tc weight staging missing or weight tensor too large");
+    char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<uintptr_t>(wws), 1024));
+    if ((size_t)(base - (char*)wws) + 2 * w_b > wws_bytes) { set_error("tcgen05 weight staging too small"); return DDN_EWORKSPACE; }
+    __nv_bfloat16* ph = (__nv_bfloat16*)base; __nv_bfloat16* pl = (__nv_bfloat16*)(base + w_b);
+    int wblocks = (int)std::min<int64_t>(ceil_div((int64_t)wel, 256), 4096);
+    DDN_LAUNCH(pack_weights_tc_kernel, wblocks, 256, 0, st, w_oihw, ph, pl, Cout, Cin, k, dgrad, want_lo);
+    b_hi = ph; b_lo = pl;
+  }
   const int block_n = gout % 128 == 0 ? 128 : 64;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  DDN_TRY(make_act_map(&ma_hi, in.hi, N, H, W, gin));
-  DDN_TRY(make_act_map(&ma_lo, want_lo ? in.lo : in.hi, N, H, W, gin));
+  DDN_TRY(make_act_map(&ma_hi, in.hi, N, H, W, gin, TC_TH, stride));
+  DDN_TRY(make_act_map(&ma_lo, want_lo ? in.lo : in.hi, N, H, W, gin, TC_TH, stride));
   DDN_TRY(make_weight_map(&mb_hi, b_hi, gout, k * k * gin, block_n));
   DDN_TRY(make_weight_map(&mb_lo, want_lo ? b_lo : b_hi, gout, k * k * gin, block_n));
   TcConvParams p;
-  p.out = out; p.addend = addend; p.N = N; p.H = H; p.W = W; p.Cin = gin; p.Cout = gout; p.taps_w = k; p.dil = dil;
-  p.tiles_h = (int)ceil_div(H, TC_TH); p.tiles_w = (int)ceil_div(W, TC_TW);
+  p.out = out; p.addend = addend; p.N = N; p.H = Ho; p.W = Wo; p.Cin = gin; p.Cout = gout; p.taps_w = k; p.dil = dil;
+  p.stride = stride;
+  p.tiles_h = (int)ceil_div(Ho, TC_TH); p.tiles_w = (int)ceil_div(Wo, TC_TW);
   p.bn_partial = bn_partial;
   ProfScope ps(dgrad ? PROF_CONV_DGRAD_TC : PROF_CONV_FWD_TC, fl, st);   // times the MMA kernel only
   if (want_lo) {
@@ -712,40 +830,77 @@ int tc_conv_planes(TcPlanes in, const float* w_oihw, float* out, const float* ad
   return launch_tc<64, 1>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);
 }
 
-// ---- fp32-tensor wrappers (single-operator C ABI): split into the staging region, then run the plane kernels
-// staging layout: [weights hi|lo][x hi|lo][dy hi|lo]
-size_t tc_workspace_bytes(size_t max_act_elems) { return tc_weight_ws_bytes() + 4 * align_up(max_act_elems * 2, 1024) + 2048; }
+// data gradient of a stride-2 conv: zero-insert dY [N,H/2,W/2,Cout] into `up` planes [N,H,W,Cout], then a stride-1 dgrad
+int tc_dgrad_strided(const float* dy_f32, TcPlanes up, const float* w_oihw, float* dx, const float* addend,
+                     int N, int H, int W, int Cin, int Cout, int k, int precision, void* wws, size_t wws_bytes, cudaStream_t st) {
+  DDN_TRY(tc_upsample_zero_split(dy_f32, const_cast<__nv_bfloat16*>(up.hi), const_cast<__nv_bfloat16*>(up.lo), N, H / 2, W / 2, Cout,
+                                 precision, st));
+  return tc_conv_planes(up, w_oihw, nullptr, dx, addend, nullptr, N, H, W, Cin, Cout, k, 1, 1, 1, precision, wws, wws_bytes, st);
+}
 
-static int stage_planes(void* ws, size_t ws_bytes, size_t x_el, size_t dy_el, void** wws, TcPlanes* x, TcPlanes* dy) {
-  char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<uintptr_t>(ws), 1024));
-  const size_t wb = tc_weight_ws_bytes(), xb = align_up(x_el * 2, 1024), yb = align_up(dy_el * 2, 1024);
-  if ((size_t)(base - (char*)ws) + wb + 2 * xb + 2 * yb > ws_bytes) { set_error("tcgen05 staging workspace too small"); return DDN_EWORKSPACE; }
-  *wws = base;
-  char* q = base + align_up(wb, 1024);
-  x->hi = (__nv_bfloat16*)q; x->lo = (__nv_bfloat16*)(q + xb);
-  dy->hi = (__nv_bfloat16*)(q + 2 * xb); dy->lo = (__nv_bfloat16*)(q + 2 * xb + yb);
+// ---- stem (conv1 7x7/2, Cin = 3) as a K = 192 GEMM over patch planes
+int tc_stem_forward(TcPlanes patches, const float* w_conv1, float* raw, float* bn_partial, int N, int H1, int W1, int precision,
+                    void* wws, size_t wws_bytes, cudaStream_t st) {
+  char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<uintptr_t>(wws), 1024));
+  DDN_CHECK_ARG((size_t)(base - (char*)wws) + 2 * 64 * 192 * 2 + 1024 <= wws_bytes, "weight staging too small");
+  __nv_bfloat16* ph = (__nv_bfloat16*)base; __nv_bfloat16* pl = (__nv_bfloat16*)(base + align_up((size_t)64 * 192 * 2, 1024));
+  DDN_LAUNCH(stem_pack_weights_kernel, (64 * 192 + 255) / 256, 256, 0, st, w_conv1, ph, pl, precision == DDN_PRECISION_BF16X3 ? 1 : 0);
+  TcPlanes wpk{ph, pl};
+  return tc_conv_planes(patches, nullptr, &wpk, raw, nullptr, bn_partial, N, H1, W1, 192, 64, 1, 1, 1, 0, precision, wws, wws_bytes, st);
+}
+
+// d conv1.weight [64,3,7,7] from the patch planes and the planes of d(raw stem output); scratch: 2 x 64*192 floats
+int tc_stem_wgrad(TcPlanes patches, TcPlanes dy, float* dw_conv1, int N, int H1, int W1, int precision, float* scratch, cudaStream_t st) {
+  float* dwp = scratch; float* dwk = scratch + 64 * 192;
+  DDN_TRY(tc_wgrad_planes(patches, dy, dwk, N, H1, W1, 192, 64, 1, 1, 1, precision, dwp, st));
+  DDN_LAUNCH(stem_unpack_wgrad_kernel, (64 * 147 + 255) / 256, 256, 0, st, dwk, dw_conv1);
   return 0;
 }
 
-int tc_conv_forward(const float* x, const float* w, float* y, int N, int H, int W, int Cin, int Cout, int k, int pad, int dil,
+// ---- fp32-tensor wrappers (single-operator C ABI): split into the staging region, then run the plane kernels
+// staging layout: [weights hi|lo][x hi|lo][dy hi|lo][zero-inserted dy hi|lo (stride 2 only)]
+size_t tc_workspace_bytes(size_t max_act_elems) { return tc_weight_ws_bytes() + 6 * align_up(max_act_elems * 2, 1024) + 4096; }
+
+static int stage_planes(void* ws, size_t ws_bytes, size_t x_el, size_t dy_el, size_t up_el, void** wws, TcPlanes* x, TcPlanes* dy,
+                        TcPlanes* up) {
+  char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<uintptr_t>(ws), 1024));
+  const size_t wb = align_up(tc_weight_ws_bytes(), 1024), xb = align_up(x_el * 2, 1024), yb = align_up(dy_el * 2, 1024),
+               ub = align_up(up_el * 2, 1024);
+  if ((size_t)(base - (char*)ws) + wb + 2 * xb + 2 * yb + 2 * ub > ws_bytes) { set_error("tcgen05 staging workspace too small"); return DDN_EWORKSPACE; }
+  *wws = base;
+  char* q = base + wb;
+  x->hi = (__nv_bfloat16*)q; x->lo = (__nv_bfloat16*)(q + xb);
+  dy->hi = (__nv_bfloat16*)(q + 2 * xb); dy->lo = (__nv_bfloat16*)(q + 2 * xb + yb);
+  up->hi = (__nv_bfloat16*)(q + 2 * xb + 2 * yb); up->lo = (__nv_bfloat16*)(q + 2 * xb + 2 * yb + ub);
+  return 0;
+}
+
+int tc_conv_forward(const float* x, const float* w, float* y, int N, int H, int W, int Cin, int Cout, int k, int stride, int pad, int dil,
                     int precision, void* ws, size_t ws_bytes, cudaStream_t st) {
   (void)pad;
-  void* wws; TcPlanes px, pdy;
-  DDN_TRY(stage_planes(ws, ws_bytes, (size_t)N * H * W * Cin, 0, &wws, &px, &pdy));
+  void* wws; TcPlanes px, pdy, pup;
+  DDN_TRY(stage_planes(ws, ws_bytes, (size_t)N * H * W * Cin, 0, 0, &wws, &px, &pdy, &pup));
   DDN_TRY(tc_split(x, const_cast<__nv_bfloat16*>(px.hi), const_cast<__nv_bfloat16*>(px.lo), (int64_t)N * H * W * Cin, precision, st));
-  return tc_conv_planes(px, w, y, nullptr, nullptr, N, H, W, Cin, Cout, k, dil, 0, precision, wws, tc_weight_ws_bytes(), st);
+  return tc_conv_planes(px, w, nullptr, y, nullptr, nullptr, N, H, W, Cin, Cout, k, stride, dil, 0, precision, wws, tc_weight_ws_bytes(), st);
 }
 
 int tc_conv_backward(const float* x, const float* w, const float* dy, float* dx, const float* dx_addend, float* dw,
-                     int N, int H, int W, int Cin, int Cout, int k, int pad, int dil, int precision,
+                     int N, int H, int W, int Cin, int Cout, int k, int stride, int pad, int dil, int precision,
                      void* ws, size_t ws_bytes, float* dwp_scratch, cudaStream_t st) {
   (void)pad;
-  void* wws; TcPlanes px, pdy;
-  DDN_TRY(stage_planes(ws, ws_bytes, (size_t)N * H * W * Cin, (size_t)N * H * W * Cout, &wws, &px, &pdy));
+  const int Ho = H / stride, Wo = W / stride;
+  void* wws; TcPlanes px, pdy, pup;
+  DDN_TRY(stage_planes(ws, ws_bytes, (size_t)N * H * W * Cin, (size_t)N * Ho * Wo * Cout, stride == 2 ? (size_t)N * H * W * Cout : 0,
+                       &wws, &px, &pdy, &pup));
   DDN_TRY(tc_split(x, const_cast<__nv_bfloat16*>(px.hi), const_cast<__nv_bfloat16*>(px.lo), (int64_t)N * H * W * Cin, precision, st));
-  DDN_TRY(tc_split(dy, const_cast<__nv_bfloat16*>(pdy.hi), const_cast<__nv_bfloat16*>(pdy.lo), (int64_t)N * H * W * Cout, precision, st));
-  DDN_TRY(tc_wgrad_planes(px, pdy, dw, N, H, W, Cin, Cout, k, dil, precision, dwp_scratch, st));
-  if (dx) DDN_TRY(tc_conv_planes(pdy, w, dx, dx_addend, nullptr, N, H, W, Cin, Cout, k, dil, 1, precision, wws, tc_weight_ws_bytes(), st));
+  DDN_TRY(tc_split(dy, const_cast<__nv_bfloat16*>(pdy.hi), const_cast<__nv_bfloat16*>(pdy.lo), (int64_t)N * Ho * Wo * Cout, precision, st));
+  DDN_TRY(tc_wgrad_planes(px, pdy, dw, N, H, W, Cin, Cout, k, stride, dil, precision, dwp_scratch, st));
+  if (dx) {
+    if (stride == 2)
+      DDN_TRY(tc_dgrad_strided(dy, pup, w, dx, dx_addend, N, H, W, Cin, Cout, k, precision, wws, tc_weight_ws_bytes(), st));
+    else
+      DDN_TRY(tc_conv_planes(pdy, w, nullptr, dx, dx_addend, nullptr, N, H, W, Cin, Cout, k, 1, dil, 1, precision, wws, tc_weight_ws_bytes(), st));
+  }
   return 0;
 }
 

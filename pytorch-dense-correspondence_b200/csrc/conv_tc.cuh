@@ -7,25 +7,32 @@ namespace ddn {
 struct TcPlanes { const __nv_bfloat16* hi; const __nv_bfloat16* lo; };   // x ~= hi + lo (lo unused in single-pass bf16)
 
 bool tc_available();
-// 3x3 (pad == dil) or 1x1 (pad 0), stride 1, Cin and Cout multiples of 64
+// forward / weight gradient: 3x3 (pad == dil) or 1x1 (pad 0), Cin and Cout multiples of 64, stride 1 (any dil) or 2 (dil 1)
 bool tc_conv_supported(int Cin, int Cout, int k, int stride, int pad, int dil, int H, int W);
 size_t tc_weight_ws_bytes();                       // staging for one conv's packed bf16 weights
 size_t tc_workspace_bytes(size_t max_act_elems);   // staging for the fp32-tensor wrappers below
-int tc_bn_partial_blocks(int N, int H, int W);     // rows of the BN partial-sum buffer a forward conv writes
+int tc_bn_partial_blocks(int N, int Ho, int Wo);   // rows of the BN partial-sum buffer a forward conv writes
 int tc_split(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t n, int precision, cudaStream_t st);
 
 // plane-level entry points (what the network engine calls)
-int tc_conv_planes(TcPlanes in, const float* w_oihw, float* out, const float* addend, float* bn_partial,
-                   int N, int H, int W, int Cin, int Cout, int k, int dil, int dgrad, int precision,
+int tc_conv_planes(TcPlanes in, const float* w_oihw, const TcPlanes* w_packed, float* out, const float* addend, float* bn_partial,
+                   int N, int H, int W, int Cin, int Cout, int k, int stride, int dil, int dgrad, int precision,
                    void* wws, size_t wws_bytes, cudaStream_t st);
-int tc_wgrad_planes(TcPlanes x, TcPlanes dy, float* dw, int N, int H, int W, int Cin, int Cout, int k, int dil,
+int tc_dgrad_strided(const float* dy_f32, TcPlanes up, const float* w_oihw, float* dx, const float* addend,
+                     int N, int H, int W, int Cin, int Cout, int k, int precision, void* wws, size_t wws_bytes, cudaStream_t st);
+int tc_wgrad_planes(TcPlanes x, TcPlanes dy, float* dw, int N, int H, int W, int Cin, int Cout, int k, int stride, int dil,
                     int precision, float* dwp, cudaStream_t st);
+// stem conv1 (7x7/2, Cin = 3) as a K = 192 GEMM over patch planes [N,H1,W1,192]
+int tc_stem_patches(const float* x_nchw, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int H, int W, int precision, cudaStream_t st);
+int tc_stem_forward(TcPlanes patches, const float* w_conv1, float* raw, float* bn_partial, int N, int H1, int W1, int precision,
+                    void* wws, size_t wws_bytes, cudaStream_t st);
+int tc_stem_wgrad(TcPlanes patches, TcPlanes dy, float* dw_conv1, int N, int H1, int W1, int precision, float* scratch, cudaStream_t st);
 
 // fp32-tensor wrappers (single-operator C ABI)
 int tc_conv_forward(const float* x_nhwc, const float* w_oihw, float* y_nhwc, int N, int H, int W, int Cin, int Cout,
-                    int k, int pad, int dil, int precision, void* ws, size_t ws_bytes, cudaStream_t st);
+                    int k, int stride, int pad, int dil, int precision, void* ws, size_t ws_bytes, cudaStream_t st);
 int tc_conv_backward(const float* x_nhwc, const float* w_oihw, const float* dy_nhwc, float* dx_nhwc, const float* dx_addend,
-                     float* dw_oihw, int N, int H, int W, int Cin, int Cout, int k, int pad, int dil, int precision,
+                     float* dw_oihw, int N, int H, int W, int Cin, int Cout, int k, int stride, int pad, int dil, int precision,
                      void* ws, size_t ws_bytes, float* dwp_scratch, cudaStream_t st);
 
 }  // namespace ddn

@@ -158,7 +158,7 @@ struct Plan {
   int B, H, W, D, training, precision;
   int H1, W1, Hp, Wp;
   size_t x4, stem_raw, stem_mean, stem_invstd, pool_out, argmax;
-  PlaneBufs pool_p, grad_p;           // planes of the pooled stem output; planes of the current d(raw conv output)
+  PlaneBufs pool_p, grad_p, patch_p;  // pooled stem output; current d(raw conv output); 7x7/2 stem patches [B,H1,W1,192]
   size_t wws;                         // packed-weight staging of the tensor-core convs
   bool tc;
   std::vector<BlockBufs> blk;
@@ -191,6 +191,7 @@ static int make_plan(Plan* p, int B, int H, int W, int D, int training, int prec
   p->tc = precision != DDN_PRECISION_FP32_SIMT;
   auto planes = [&](int64_t n) { PlaneBufs pb{0, 0}; if (p->tc) { pb.hi = alloc(2 * (size_t)n); pb.lo = alloc(2 * (size_t)n); } return pb; };
   p->pool_p = planes((int64_t)B * p->Hp * p->Wp * 64);
+  p->patch_p = planes((int64_t)B * p->H1 * p->W1 * 192);
   int h = p->Hp, w = p->Wp;
   size_t max_w = 0;
   int64_t max_act = (int64_t)B * p->H1 * p->W1 * 64;
@@ -226,7 +227,7 @@ static int make_plan(Plan* p, int B, int H, int W, int D, int training, int prec
   for (int C : {64, 128, 256, 512}) {
     int64_t Mmax = C == 64 ? (int64_t)B * p->H1 * p->W1 : (int64_t)B * p->Hp * p->Wp;
     max_partial = std::max<int64_t>(max_partial, 2ll * bn_partial_blocks(Mmax, C) * C + 2 * C);
-    int hh = C == 64 ? p->Hp : p->Hp / 2, ww = C == 64 ? p->Wp : p->Wp / 2;     // tcgen05 convs write one row per 8x16 tile
+    int hh = C == 64 ? p->H1 : p->Hp / 2, ww = C == 64 ? p->W1 : p->Wp / 2;     // tcgen05 convs write one row per 8x16 tile
     max_partial = std::max<int64_t>(max_partial, 2ll * tc_bn_partial_blocks(B, hh, ww) * C + 2 * C);
   }
   p->partial = f32(max_partial * 2);
@@ -261,10 +262,10 @@ static int conv_bn_forward(const Ctx& c, const ConvSpec& cs, const BnSpec& bs, c
   float* rm = c.buffers + bs.rm_off; float* rv = c.buffers + bs.rv_off;
   if (conv_on_tc(c, cs, cb.Hin, cb.Win)) {
     float* partial = c.training ? c.f(c.p->partial) : nullptr;
-    DDN_TRY(tc_conv_planes(c.planes(in_p), w, raw, nullptr, partial, N, cb.Hin, cb.Win, cs.cin, cs.cout, cs.k, cs.dil, 0,
-                           c.p->precision, c.ws + c.p->wws, tc_weight_ws_bytes(), c.st));
+    DDN_TRY(tc_conv_planes(c.planes(in_p), w, nullptr, raw, nullptr, partial, N, cb.Hin, cb.Win, cs.cin, cs.cout, cs.k, cs.stride,
+                           cs.dil, 0, c.p->precision, c.ws + c.p->wws, tc_weight_ws_bytes(), c.st));
     if (c.training)
-      return launch_bn_stats_finalize(partial, tc_bn_partial_blocks(N, cb.Hin, cb.Win), M, bs.C, c.f(cb.mean), c.f(cb.invstd),
+      return launch_bn_stats_finalize(partial, tc_bn_partial_blocks(N, cb.Hout, cb.Wout), M, bs.C, c.f(cb.mean), c.f(cb.invstd),
                                       rm, rv, c.momentum, c.eps, c.st);
     return launch_bn_eval_stats(rm, rv, bs.C, c.eps, c.f(cb.mean), c.f(cb.invstd), c.st);
   }
@@ -284,9 +285,22 @@ static int net_forward(const Ctx& c, const float* x, float* y) {
   const NetSpec& s = *c.s; const Plan& p = *c.p;
   const int B = p.B;
   // stem: conv1 7x7/2 -> bn1 -> relu -> maxpool 3x3/2          (resnet.py:232-235)
-  DDN_TRY(launch_nchw_to_nhwc4(x, c.f(p.x4), B, p.H, p.W, c.st));
   ConvBufs stem_cb{p.stem_raw, p.stem_mean, p.stem_invstd, p.H, p.W, p.H1, p.W1};
-  DDN_TRY(conv_bn_forward(c, s.stem, s.stem_bn, c.f(p.x4), PlaneBufs{0, 0}, stem_cb, B, 4));
+  if (p.tc) {   // conv1 as a K = 192 GEMM over 7x7/2 patch planes, BN statistics from the conv epilogue
+    DDN_TRY(tc_stem_patches(x, c.h(p.patch_p.hi), c.h(p.patch_p.lo), B, p.H, p.W, p.precision, c.st));
+    float* partial = c.training ? c.f(p.partial) : nullptr;
+    DDN_TRY(tc_stem_forward(c.planes(p.patch_p), c.params + s.stem.w_off, c.f(p.stem_raw), partial, B, p.H1, p.W1, p.precision,
+                            c.ws + p.wws, tc_weight_ws_bytes(), c.st));
+    float* rm = c.buffers + s.stem_bn.rm_off; float* rv = c.buffers + s.stem_bn.rv_off;
+    if (c.training)
+      DDN_TRY(launch_bn_stats_finalize(partial, tc_bn_partial_blocks(B, p.H1, p.W1), (int64_t)B * p.H1 * p.W1, 64,
+                                       c.f(p.stem_mean), c.f(p.stem_invstd), rm, rv, c.momentum, c.eps, c.st));
+    else
+      DDN_TRY(launch_bn_eval_stats(rm, rv, 64, c.eps, c.f(p.stem_mean), c.f(p.stem_invstd), c.st));
+  } else {
+    DDN_TRY(launch_nchw_to_nhwc4(x, c.f(p.x4), B, p.H, p.W, c.st));
+    DDN_TRY(conv_bn_forward(c, s.stem, s.stem_bn, c.f(p.x4), PlaneBufs{0, 0}, stem_cb, B, 4));
+  }
   DDN_TRY(launch_stem_bn_relu_pool(c.f(p.stem_raw), c.f(p.stem_mean), c.f(p.stem_invstd), c.params + s.stem_bn.g_off,
                                    c.params + s.stem_bn.b_off, c.f(p.pool_out), reinterpret_cast<uint8_t*>(c.ws + p.argmax),
                                    p.tc ? c.h(p.pool_p.hi) : nullptr, p.tc ? c.h(p.pool_p.lo) : nullptr,
@@ -332,11 +346,16 @@ static int conv_backward(const Ctx& c, const ConvSpec& cs, const float* in, cons
   float* dw = c.grads + cs.w_off;
   const double fl = 2.0 * N * Hout * Wout * (double)cs.cout * cs.k * cs.k * cs.cin;
   if (conv_on_tc(c, cs, Hin, Win)) {
-    DDN_TRY(tc_wgrad_planes(c.planes(in_p), c.planes(p.grad_p), dw, N, Hin, Win, cs.cin, cs.cout, cs.k, cs.dil, p.precision,
-                            c.f(p.dwp), c.st));
-    if (dx)
-      DDN_TRY(tc_conv_planes(c.planes(p.grad_p), w, dx, addend, nullptr, N, Hin, Win, cs.cin, cs.cout, cs.k, cs.dil, 1,
-                             p.precision, c.ws + p.wws, tc_weight_ws_bytes(), c.st));
+    DDN_TRY(tc_wgrad_planes(c.planes(in_p), c.planes(p.grad_p), dw, N, Hin, Win, cs.cin, cs.cout, cs.k, cs.stride, cs.dil,
+                            p.precision, c.f(p.dwp), c.st));
+    if (dx) {
+      if (cs.stride == 2)   // zero-insert the fp32 dY into the (now free) gradient planes, then an ordinary stride-1 dgrad
+        DDN_TRY(tc_dgrad_strided(dy, c.planes(p.grad_p), w, dx, addend, N, Hin, Win, cs.cin, cs.cout, cs.k, p.precision,
+                                 c.ws + p.wws, tc_weight_ws_bytes(), c.st));
+      else
+        DDN_TRY(tc_conv_planes(c.planes(p.grad_p), w, nullptr, dx, addend, nullptr, N, Hin, Win, cs.cin, cs.cout, cs.k, 1, cs.dil, 1,
+                               p.precision, c.ws + p.wws, tc_weight_ws_bytes(), c.st));
+    }
     return 0;
   }
   ConvGeom g;
@@ -361,7 +380,7 @@ static int conv_backward(const Ctx& c, const ConvSpec& cs, const float* in, cons
 // BN backward whose dx feeds `cs`'s backward: planes for a tensor-core conv, fp32 for a SIMT conv
 static int bn_backward_for(const Ctx& c, BnBwdArgs a, const ConvSpec& cs, int Hin, int Win, float* dx_f32) {
   if (conv_on_tc(c, cs, Hin, Win)) {
-    a.dx = nullptr;
+    a.dx = cs.stride == 2 ? dx_f32 : nullptr;      // the strided data gradient re-reads dY in fp32 (zero insertion)
     a.dx_hi = c.h(c.p->grad_p.hi);
     a.dx_lo = c.p->precision == DDN_PRECISION_BF16X3 ? c.h(c.p->grad_p.lo) : nullptr;
   } else {
@@ -420,6 +439,11 @@ static int net_backward(const Ctx& c, const float* dy) {
   BnBwdArgs ks = {S[t1], nullptr, c.f(p.stem_raw), c.f(p.stem_mean), c.f(p.stem_invstd), c.params + s.stem_bn.g_off,
                   S[t2], c.grads + s.stem_bn.g_off, c.grads + s.stem_bn.b_off, nullptr, c.f(p.partial),
                   (int64_t)B * p.H1 * p.W1, 64, 0, 1, nullptr, nullptr};
+  if (p.tc) {
+    ks.dx = nullptr; ks.dx_hi = c.h(p.grad_p.hi); ks.dx_lo = p.precision == DDN_PRECISION_BF16X3 ? c.h(p.grad_p.lo) : nullptr;
+    DDN_TRY(launch_bn_backward(ks, c.st));
+    return tc_stem_wgrad(c.planes(p.patch_p), c.planes(p.grad_p), c.grads + s.stem.w_off, B, p.H1, p.W1, p.precision, c.f(p.dwp), c.st);
+  }
   DDN_TRY(launch_bn_backward(ks, c.st));
   DDN_TRY(conv_backward(c, s.stem, c.f(p.x4), PlaneBufs{0, 0}, S[t2], nullptr, nullptr, B, p.H, p.W, p.H1, p.W1, 4));
   return 0;
@@ -528,7 +552,7 @@ extern "C" int ddn_conv2d_forward(const float* x, const float* w, float* y, int 
   int Ho = conv_out(H, k, stride, pad, dil), Wo = conv_out(W, k, stride, pad, dil);
   if (precision != DDN_PRECISION_FP32_SIMT) {
     DDN_CHECK_ARG(tc_conv_supported(Cin, Cout, k, stride, pad, dil, H, W), "shape not supported by the tcgen05 path");
-    return tc_conv_forward(x, w, y, N, H, W, Cin, Cout, k, pad, dil, precision, (char*)workspace + 3 * wb,
+    return tc_conv_forward(x, w, y, N, H, W, Cin, Cout, k, stride, pad, dil, precision, (char*)workspace + 3 * wb,
                            workspace_bytes - 3 * wb, st);
   }
   ConvGeom g;
@@ -549,7 +573,7 @@ extern "C" int ddn_conv2d_backward(const float* x, const float* w, const float* 
   float* wp = (float*)workspace; float* dwp = (float*)((char*)workspace + wb);
   if (precision != DDN_PRECISION_FP32_SIMT) {
     DDN_CHECK_ARG(tc_conv_supported(Cin, Cout, k, stride, pad, dil, H, W), "shape not supported by the tcgen05 path");
-    return tc_conv_backward(x, w, dy, dx, nullptr, dw, N, H, W, Cin, Cout, k, pad, dil, precision,
+    return tc_conv_backward(x, w, dy, dx, nullptr, dw, N, H, W, Cin, Cout, k, stride, pad, dil, precision,
                             (char*)workspace + 3 * wb, workspace_bytes - 3 * wb, dwp, st);
   }
   ConvGeom g;

@@ -61,6 +61,9 @@ TC_CASES = [c for c in CONV_CASES if c[6] == 1] + [
     (2, 60, 80, 512, 512, 3, 1, 4, 4),     # the dominant GEMM: 72 k-blocks, 4 N-tiles
     (1, 8, 12, 512, 512, 3, 1, 4, 4),      # feature map smaller than one 8x16 tile
     (1, 60, 80, 128, 256, 1, 1, 0, 1),     # 1x1 downsample (layer3.0)
+    (2, 30, 40, 64, 128, 3, 2, 1, 1),      # layer2.0.conv1: stride 2 through TMA element strides; dgrad by zero insertion
+    (1, 30, 40, 64, 128, 1, 2, 0, 1),      # layer2.0.downsample: 1x1 stride 2
+    (1, 120, 160, 64, 128, 3, 2, 1, 1),    # the real layer2.0.conv1 size
 ]
 
 
