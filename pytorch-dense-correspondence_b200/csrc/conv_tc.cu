@@ -18,6 +18,7 @@
 // Reference op replaced: nn.Conv2d via conv3x3 (PSD/vision/torchvision/models/resnet.py:20-37,45,48) and the
 // stride-1 1x1 downsample convs (resnet.py:210-214), plus their autograd data gradient.
 #include <cuda.h>
+#include <cstdlib>
 
 #include "conv.cuh"
 #include "conv_tc.cuh"
@@ -299,6 +300,193 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   }
 }
 
+
+
+// ------------------------------------------------------------------------------------------------ persistent variant
+// Same tile computation as conv_tc_kernel, but one CTA per SM loops over tiles (static round-robin, tile = spatial-major so
+// the CTAs working on the Cout slices of one pixel tile share its A loads in L2) with TWO TMEM accumulators: while the
+// epilogue warps drain accumulator i (TMEM -> registers -> global, BN column sums) the MMA warp is already filling
+// accumulator i+1 and the TMA warp runs ahead through the shared-memory ring.  TMEM allocation, barrier setup and
+// descriptor prefetch are paid once per SM instead of once per tile.
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int BLOCK_N, int NPROD>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                          const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                          const TcConvParams p) {
+  constexpr int NSPLIT = NPROD == 3 ? 2 : 1;
+  constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
+  constexpr int STAGE_BYTES = NSPLIT * (TC_A_BYTES + B_BYTES);
+  constexpr int STAGES = (192 * 1024) / STAGE_BYTES >= 8 ? 8 : (192 * 1024) / STAGE_BYTES;
+  static_assert(STAGES >= 2, "pipeline needs at least two stages");
+  constexpr uint32_t IDESC = make_idesc_bf16(128, BLOCK_N);
+  constexpr int NCOLS = 2 * BLOCK_N;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t acc_full[2];
+  __shared__ __align__(8) uint64_t acc_empty[2];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_part[2][2][4][BLOCK_N];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_co = p.Cout / BLOCK_N;
+  const int n_sp = p.N * p.tiles_h * p.tiles_w;
+  const int total_tiles = n_sp * n_co;
+  const int cin_chunks = p.Cin / TC_BLOCK_K;
+  const int num_kb = p.taps_w * p.taps_w * cin_chunks;
+  const int half = p.taps_w >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&acc_full[b]), 1); mbar_init(smem_u32(&acc_empty[b]), 4); }
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_b_hi);
+    if (NSPLIT == 2) { tma_prefetch_desc(&tm_a_lo); tma_prefetch_desc(&tm_b_lo); }
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(NCOLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      uint32_t g = 0;                                  // global k-block counter across tiles -> ring slot / phase
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int co0 = (tile % n_co) * BLOCK_N;
+        int t = tile / n_co;
+        const int tw = t % p.tiles_w; t /= p.tiles_w;
+        const int th = t % p.tiles_h; const int n = t / p.tiles_h;
+        const int h0 = th * TC_TH, w0 = tw * TC_TW;
+        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+          const int s = g % STAGES;
+          mbar_wait(smem_u32(&empty_bar[s]), ((g / STAGES) & 1) ^ 1);
+          const int tap = kb / cin_chunks, cc = kb - tap * cin_chunks;
+          const int r = tap / p.taps_w, sx = tap - r * p.taps_w;
+          const int hh = h0 * p.stride + (r - half) * p.dil, ww = w0 * p.stride + (sx - half) * p.dil;
+          uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+          const uint32_t bar = smem_u32(&full_bar[s]);
+          mbar_expect_tx(bar, STAGE_BYTES);
+          tma_load_4d(smem_u32(st), &tm_a_hi, bar, cc * TC_BLOCK_K, ww, hh, n);
+          tma_load_2d(smem_u32(st + NSPLIT * TC_A_BYTES), &tm_b_hi, bar, kb * TC_BLOCK_K, co0);
+          if (NSPLIT == 2) {
+            tma_load_4d(smem_u32(st + TC_A_BYTES), &tm_a_lo, bar, cc * TC_BLOCK_K, ww, hh, n);
+            tma_load_2d(smem_u32(st + 2 * TC_A_BYTES + B_BYTES), &tm_b_lo, bar, kb * TC_BLOCK_K, co0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      uint32_t g = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(smem_u32(&acc_empty[buf]), ((it >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)(buf * BLOCK_N);
+        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+          const int s = g % STAGES;
+          mbar_wait(smem_u32(&full_bar[s]), (g / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + (size_t)s * STAGE_BYTES);
+          const uint64_t a_hi = make_kmajor_sw128_desc(st);
+          const uint64_t b_hi = make_kmajor_sw128_desc(st + NSPLIT * TC_A_BYTES);
+          const uint64_t a_lo = make_kmajor_sw128_desc(st + TC_A_BYTES);
+          const uint64_t b_lo = make_kmajor_sw128_desc(st + 2 * TC_A_BYTES + B_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
+            const uint64_t adv = (uint64_t)((k * 32) >> 4);
+            if (NPROD == 3) {
+              umma_bf16(acc, a_hi + adv, b_lo + adv, IDESC, (kb | k) != 0);
+              umma_bf16(acc, a_lo + adv, b_hi + adv, IDESC, 1);
+              umma_bf16(acc, a_hi + adv, b_hi + adv, IDESC, 1);
+            } else {
+              umma_bf16(acc, a_hi + adv, b_hi + adv, IDESC, (kb | k) != 0);
+            }
+          }
+          umma_commit(smem_u32(&empty_bar[s]));
+        }
+        umma_commit(smem_u32(&acc_full[buf]));
+      }
+    }
+  } else {
+    // ===== epilogue warps =====
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int co0 = (tile % n_co) * BLOCK_N;
+      const int sp = tile / n_co;
+      int t = sp;
+      const int tw = t % p.tiles_w; t /= p.tiles_w;
+      const int th = t % p.tiles_h; const int n = t / p.tiles_h;
+      const int h = th * TC_TH + row / TC_TW, w = tw * TC_TW + row % TC_TW;
+      const bool ok = h < p.H && w < p.W;
+      const size_t pix = ((size_t)n * p.H + (ok ? h : 0)) * p.W + (ok ? w : 0);
+      float* o = p.out + pix * p.Cout + co0;
+      const float* ad = p.addend ? p.addend + pix * p.Cout + co0 : nullptr;
+      mbar_wait(smem_u32(&acc_full[buf]), (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BLOCK_N + c * 32), v);
+        if (ok) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 f = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            if (ad) {
+              float4 a = __ldg(reinterpret_cast<const float4*>(ad + c * 32 + j));
+              f.x += a.x; f.y += a.y; f.z += a.z; f.w += a.w;
+            }
+            *reinterpret_cast<float4*>(o + c * 32 + j) = f;
+          }
+        }
+        if (p.bn_partial) {
+          float a[32], b[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { a[j] = ok ? __uint_as_float(v[j]) : 0.f; b[j] = a[j] * a[j]; }
+          warp_colsum32(a, lane);
+          warp_colsum32(b, lane);
+          s_part[buf][0][q][c * 32 + lane] = a[0];
+          s_part[buf][1][q][c * 32 + lane] = b[0];
+        }
+      }
+      // the accumulator is in registers / memory now: hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
+      if (p.bn_partial) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int e = threadIdx.x - 64;
+        if (e < BLOCK_N) {
+          const float s0 = s_part[buf][0][0][e] + s_part[buf][0][1][e] + s_part[buf][0][2][e] + s_part[buf][0][3][e];
+          const float s1 = s_part[buf][1][0][e] + s_part[buf][1][1][e] + s_part[buf][1][2][e] + s_part[buf][1][3][e];
+          p.bn_partial[(size_t)sp * p.Cout + co0 + e] = s0;
+          p.bn_partial[((size_t)n_sp + sp) * p.Cout + co0 + e] = s1;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(NCOLS));
+  }
+}
 
 // ------------------------------------------------------------------------------------------------ weight gradient
 // dW[co][tap][ci] = sum_pixels dY[pixel][co] * X[pixel + offset(tap)][ci]  as a tcgen05 GEMM with the PIXELS as the K
@@ -776,6 +964,21 @@ static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUt
   if (!configured) {
     DDN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
+  }
+  static int persistent = -1;
+  if (persistent < 0) { const char* e = getenv("DDN_TC_PERSISTENT"); persistent = (e && e[0] == '0') ? 0 : 1; }
+  if (persistent) {
+    constexpr int PSTAGES = (192 * 1024) / STAGE_BYTES >= 8 ? 8 : (192 * 1024) / STAGE_BYTES;
+    const size_t psmem = (size_t)PSTAGES * STAGE_BYTES + 1024;
+    static bool pconfigured = false;
+    if (!pconfigured) {
+      DDN_CUDA(cudaFuncSetAttribute(conv_tc_persistent_kernel<BLOCK_N, NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+      pconfigured = true;
+    }
+    const int total = p.N * p.tiles_h * p.tiles_w * (p.Cout / BLOCK_N);
+    const int grid = std::min(total, num_sms());
+    DDN_LAUNCH((conv_tc_persistent_kernel<BLOCK_N, NPROD>), grid, TC_THREADS, psmem, st, a_hi, a_lo, b_hi, b_lo, p);
+    return 0;
   }
   dim3 grid((unsigned)(p.N * p.tiles_h * p.tiles_w), (unsigned)(p.Cout / BLOCK_N));
   DDN_LAUNCH((conv_tc_kernel<BLOCK_N, NPROD>), grid, TC_THREADS, smem, st, a_hi, a_lo, b_hi, b_lo, p);
