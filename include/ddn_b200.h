@@ -93,6 +93,13 @@ int ddn_resnet34_8s_backward(const float* dy, const float* params, float* grads,
                              void* workspace, size_t workspace_bytes,
                              int B, int H, int W, int D, float eps, int precision, void* stream);
 
+/* Optional cache of the tensor-core weight packs (bf16 hi/lo, forward and data-gradient layouts of every conv).
+ * The caller owns `cache` (ddn_resnet34_8s_weight_cache_bytes(D) bytes of device memory) and bumps `version` whenever the
+ * parameter array changed (optimizer step, load_state_dict); forward/backward calls made with the same `params` pointer and
+ * `precision` then pack each conv once per version instead of once per call.  cache == NULL switches it off. */
+size_t ddn_resnet34_8s_weight_cache_bytes(int D);
+int ddn_resnet34_8s_set_weight_cache(void* cache, size_t bytes, const float* params, uint64_t version, int precision);
+
 /* ------------------------------------------------------------------------------------------
  * Pixelwise contrastive loss.
  * Descriptor images are addressed with explicit strides so the reference's strided view
@@ -210,6 +217,12 @@ int ddn_upsample_bilinear_backward(const float* dy, float* dx, int NC, int h, in
 
 /* Data-parallel helpers on the flat gradient: g *= scale (after an all-reduce SUM over ranks). */
 int ddn_scale_inplace(float* g, int64_t n, float scale, void* stream);
+
+/* Fused Adam step over flat arrays == torch.optim.Adam(lr, betas, eps, weight_decay) as used by
+ * dense_correspondence/training/training.py:133-145,346 (L2 weight decay folded into the gradient, bias-corrected moments,
+ * no amsgrad).  `step` is the 1-based step count; grads are read as grads[i]*grad_scale (1/world after a SUM all-reduce). */
+int ddn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, int64_t step,
+                  float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale, void* stream);
 
 /* Per-kernel-class device timing (CUDA events recorded on the launching stream around each launch of the
  * convolution / loss kernels while enabled).  ddn_profile_read synchronises on the recorded events and

@@ -48,6 +48,8 @@ _SIGNATURES = {
     "ddn_resnet34_8s_param_count": (i64, [i32]),
     "ddn_resnet34_8s_buffer_count": (i64, []),
     "ddn_resnet34_8s_workspace_bytes": (sz, [i32, i32, i32, i32, i32, i32]),
+    "ddn_resnet34_8s_weight_cache_bytes": (sz, [i32]),
+    "ddn_resnet34_8s_set_weight_cache": (i32, [vp, sz, vp, ctypes.c_uint64, i32]),
     "ddn_resnet34_8s_forward": (i32, [vp, vp, vp, vp, vp, sz, i32, i32, i32, i32, i32, f32, f32, i32, vp]),
     "ddn_resnet34_8s_backward": (i32, [vp, vp, vp, vp, sz, i32, i32, i32, i32, f32, i32, vp]),
     "ddn_contrastive_terms_forward": (i32, [vp, vp, i64, i64, i64, i32, i64, i32, i32, ctypes.POINTER(LossTerm), i32, vp, vp, vp]),
@@ -65,6 +67,7 @@ _SIGNATURES = {
     "ddn_upsample_bilinear_forward": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "ddn_upsample_bilinear_backward": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "ddn_scale_inplace": (i32, [vp, i64, f32, vp]),
+    "ddn_adam_step": (i32, [vp, vp, vp, vp, i64, i64, f32, f32, f32, f32, f32, f32, vp]),
     "ddn_profile_enable": (i32, [i32]),
     "ddn_profile_reset": (i32, []),
     "ddn_profile_read": (i32, [ctypes.POINTER(ProfileEntry), i32]),

@@ -750,35 +750,51 @@ __global__ void upsample_zero_split_kernel(const float* __restrict__ dy, __nv_bf
 }
 
 // Stem: x fp32 NCHW [N,3,H,W] -> 7x7/2 patch planes [N,H1,W1,192] bf16 (k = (r*7+s)*3 + c for k < 147, zero above), so
-// that conv1 becomes a GEMM with K = 192 on the tensor cores.
-__global__ void stem_patch_split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                        int N, int H, int W, int H1, int W1, int want_lo) {
-  const int64_t total = (int64_t)N * H1 * W1 * 48;      // 48 quads of 4 k-values per output pixel
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int kq = (int)(i % 48); int64_t t = i / 48;
-    int wo = (int)(t % W1); t /= W1;
-    int ho = (int)(t % H1); int n = (int)(t / H1);
+// that conv1 becomes a GEMM with K = 192 on the tensor cores.  One block = one output row x 64 output columns: the 7 input
+// rows x 133 input columns x 3 channels it needs are staged in shared memory with coalesced loads, then written out as
+// 384-byte (hi) + 384-byte (lo) rows per output pixel.
+constexpr int STEM_TW = 64;
+constexpr int STEM_COLS = 2 * STEM_TW + 5;
+__global__ void __launch_bounds__(256)
+stem_patch_split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                        int N, int H, int W, int H1, int W1, int want_lo) {
+  __shared__ float tile[3][7][STEM_COLS + 1];
+  const int wt = blockIdx.x, ho = blockIdx.y, n = blockIdx.z;
+  const int wo0 = wt * STEM_TW;
+  const int h_base = 2 * ho - 3, w_base = 2 * wo0 - 3;
+  for (int i = threadIdx.x; i < 3 * 7 * STEM_COLS; i += blockDim.x) {
+    int col = i % STEM_COLS, rc = i / STEM_COLS;
+    int r = rc % 7, c = rc / 7;
+    int h = h_base + r, w = w_base + col;
+    float v = 0.f;
+    if (h >= 0 && h < H && w >= 0 && w < W) v = __ldg(x + (((int64_t)n * 3 + c) * H + h) * W + w);
+    tile[c][r][col] = v;
+  }
+  __syncthreads();
+  const int npix = min(STEM_TW, W1 - wo0);
+  for (int i = threadIdx.x; i < npix * 48; i += blockDim.x) {
+    const int kq = i % 48, px = i / 48;
     float v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      int k = kq * 4 + j;
+      const int k = kq * 4 + j;
       float val = 0.f;
       if (k < 147) {
-        int c = k % 3, rs = k / 3, r = rs / 7, s = rs - r * 7;
-        int h = 2 * ho - 3 + r, w = 2 * wo - 3 + s;
-        if (h >= 0 && h < H && w >= 0 && w < W) val = __ldg(x + (((int64_t)n * 3 + c) * H + h) * W + w);
+        const int c = k % 3, rs = k / 3, r = rs / 7, sx = rs - r * 7;
+        val = tile[c][r][2 * px + sx];
       }
       v[j] = val;
     }
+    const int64_t o = (((int64_t)n * H1 + ho) * W1 + wo0 + px) * 48 + kq;
     __nv_bfloat16 h0 = __float2bfloat16_rn(v[0]), h1 = __float2bfloat16_rn(v[1]), h2 = __float2bfloat16_rn(v[2]), h3 = __float2bfloat16_rn(v[3]);
     __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
     uint2 hv; hv.x = *reinterpret_cast<uint32_t*>(&a); hv.y = *reinterpret_cast<uint32_t*>(&b);
-    reinterpret_cast<uint2*>(hi)[i] = hv;
+    reinterpret_cast<uint2*>(hi)[o] = hv;
     if (want_lo) {
-      __nv_bfloat162 c = __halves2bfloat162(__float2bfloat16_rn(v[0] - __bfloat162float(h0)), __float2bfloat16_rn(v[1] - __bfloat162float(h1)));
-      __nv_bfloat162 d = __halves2bfloat162(__float2bfloat16_rn(v[2] - __bfloat162float(h2)), __float2bfloat16_rn(v[3] - __bfloat162float(h3)));
-      uint2 lv; lv.x = *reinterpret_cast<uint32_t*>(&c); lv.y = *reinterpret_cast<uint32_t*>(&d);
-      reinterpret_cast<uint2*>(lo)[i] = lv;
+      __nv_bfloat162 c2 = __halves2bfloat162(__float2bfloat16_rn(v[0] - __bfloat162float(h0)), __float2bfloat16_rn(v[1] - __bfloat162float(h1)));
+      __nv_bfloat162 d2 = __halves2bfloat162(__float2bfloat16_rn(v[2] - __bfloat162float(h2)), __float2bfloat16_rn(v[3] - __bfloat162float(h3)));
+      uint2 lv; lv.x = *reinterpret_cast<uint32_t*>(&c2); lv.y = *reinterpret_cast<uint32_t*>(&d2);
+      reinterpret_cast<uint2*>(lo)[o] = lv;
     }
   }
 }
@@ -937,6 +953,14 @@ int tc_split(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t n, in
   return 0;
 }
 
+int tc_pack_weights(const float* w_oihw, __nv_bfloat16* hi, __nv_bfloat16* lo, int Cout, int Cin, int k, int dgrad, int precision,
+                    cudaStream_t st) {
+  const size_t wel = (size_t)Cout * Cin * k * k;
+  int wblocks = (int)std::min<int64_t>(ceil_div((int64_t)wel, 256), 4096);
+  DDN_LAUNCH(pack_weights_tc_kernel, wblocks, 256, 0, st, w_oihw, hi, lo, Cout, Cin, k, dgrad, precision == DDN_PRECISION_BF16X3 ? 1 : 0);
+  return 0;
+}
+
 int tc_upsample_zero_split(const float* dy, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int Ho, int Wo, int C, int precision,
                            cudaStream_t st) {
   int64_t total = (int64_t)N * Ho * Wo * (C / 4);
@@ -947,9 +971,9 @@ int tc_upsample_zero_split(const float* dy, __nv_bfloat16* hi, __nv_bfloat16* lo
 
 int tc_stem_patches(const float* x_nchw, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int H, int W, int precision, cudaStream_t st) {
   const int H1 = (H - 1) / 2 + 1, W1 = (W - 1) / 2 + 1;
-  int64_t total = (int64_t)N * H1 * W1 * 48;
-  int blocks = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)num_sms() * 16);
-  DDN_LAUNCH(stem_patch_split_kernel, blocks, 256, 0, st, x_nchw, hi, lo, N, H, W, H1, W1, precision == DDN_PRECISION_BF16X3 ? 1 : 0);
+  DDN_CHECK_ARG(N <= 65535 && H1 <= 65535, "stem: batch / height too large for the launch grid");
+  dim3 grid((unsigned)ceil_div(W1, STEM_TW), (unsigned)H1, (unsigned)N);
+  DDN_LAUNCH(stem_patch_split_kernel, grid, 256, 0, st, x_nchw, hi, lo, N, H, W, H1, W1, precision == DDN_PRECISION_BF16X3 ? 1 : 0);
   return 0;
 }
 
@@ -1034,11 +1058,11 @@ int tc_conv_planes(TcPlanes in, const float* w_oihw, const TcPlanes* wpk, float*
 }
 
 // data gradient of a stride-2 conv: zero-insert dY [N,H/2,W/2,Cout] into `up` planes [N,H,W,Cout], then a stride-1 dgrad
-int tc_dgrad_strided(const float* dy_f32, TcPlanes up, const float* w_oihw, float* dx, const float* addend,
+int tc_dgrad_strided(const float* dy_f32, TcPlanes up, const float* w_oihw, const TcPlanes* w_packed, float* dx, const float* addend,
                      int N, int H, int W, int Cin, int Cout, int k, int precision, void* wws, size_t wws_bytes, cudaStream_t st) {
   DDN_TRY(tc_upsample_zero_split(dy_f32, const_cast<__nv_bfloat16*>(up.hi), const_cast<__nv_bfloat16*>(up.lo), N, H / 2, W / 2, Cout,
                                  precision, st));
-  return tc_conv_planes(up, w_oihw, nullptr, dx, addend, nullptr, N, H, W, Cin, Cout, k, 1, 1, 1, precision, wws, wws_bytes, st);
+  return tc_conv_planes(up, w_oihw, w_packed, dx, addend, nullptr, N, H, W, Cin, Cout, k, 1, 1, 1, precision, wws, wws_bytes, st);
 }
 
 // ---- stem (conv1 7x7/2, Cin = 3) as a K = 192 GEMM over patch planes
@@ -1100,7 +1124,7 @@ int tc_conv_backward(const float* x, const float* w, const float* dy, float* dx,
   DDN_TRY(tc_wgrad_planes(px, pdy, dw, N, H, W, Cin, Cout, k, stride, dil, precision, dwp_scratch, st));
   if (dx) {
     if (stride == 2)
-      DDN_TRY(tc_dgrad_strided(dy, pup, w, dx, dx_addend, N, H, W, Cin, Cout, k, precision, wws, tc_weight_ws_bytes(), st));
+      DDN_TRY(tc_dgrad_strided(dy, pup, w, nullptr, dx, dx_addend, N, H, W, Cin, Cout, k, precision, wws, tc_weight_ws_bytes(), st));
     else
       DDN_TRY(tc_conv_planes(pdy, w, nullptr, dx, dx_addend, nullptr, N, H, W, Cin, Cout, k, 1, dil, 1, precision, wws, tc_weight_ws_bytes(), st));
   }

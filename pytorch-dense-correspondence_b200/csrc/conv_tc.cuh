@@ -18,7 +18,9 @@ int tc_split(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t n, in
 int tc_conv_planes(TcPlanes in, const float* w_oihw, const TcPlanes* w_packed, float* out, const float* addend, float* bn_partial,
                    int N, int H, int W, int Cin, int Cout, int k, int stride, int dil, int dgrad, int precision,
                    void* wws, size_t wws_bytes, cudaStream_t st);
-int tc_dgrad_strided(const float* dy_f32, TcPlanes up, const float* w_oihw, float* dx, const float* addend,
+int tc_pack_weights(const float* w_oihw, __nv_bfloat16* hi, __nv_bfloat16* lo, int Cout, int Cin, int k, int dgrad, int precision,
+                    cudaStream_t st);
+int tc_dgrad_strided(const float* dy_f32, TcPlanes up, const float* w_oihw, const TcPlanes* w_packed, float* dx, const float* addend,
                      int N, int H, int W, int Cin, int Cout, int k, int precision, void* wws, size_t wws_bytes, cudaStream_t st);
 int tc_wgrad_planes(TcPlanes x, TcPlanes dy, float* dw, int N, int H, int W, int Cin, int Cout, int k, int stride, int dil,
                     int precision, float* dwp, cudaStream_t st);

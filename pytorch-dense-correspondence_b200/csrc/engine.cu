@@ -247,6 +247,35 @@ struct Ctx {
   TcPlanes planes(const PlaneBufs& b) const { return TcPlanes{h(b.hi), h(b.lo)}; }
 };
 
+// Optional caller-owned cache of the packed bf16 weights (forward and data-gradient packs of every conv): filled lazily,
+// valid for one (parameter array, version, precision) triple -- registered with ddn_resnet34_8s_set_weight_cache().
+struct WeightCache {
+  char* base = nullptr; size_t bytes = 0; uint64_t version = 0; const float* params = nullptr; int precision = -1;
+  std::vector<uint8_t> ok;
+};
+static WeightCache g_wcache;
+static std::mutex g_wcache_mu;
+
+// packed planes of conv `cs` (mode 0 = forward, 1 = data gradient) from the cache, or nullptr when no usable cache
+static const TcPlanes* cached_pack(const Ctx& c, const ConvSpec& cs, int dgrad, TcPlanes* out) {
+  std::lock_guard<std::mutex> lk(g_wcache_mu);
+  WeightCache& wc = g_wcache;
+  if (!wc.base || wc.params != c.params || wc.precision != c.p->precision) return nullptr;
+  const size_t wel = (size_t)cs.cout * cs.cin * cs.k * cs.k;
+  const size_t off = ((size_t)cs.w_off * 2 + (size_t)dgrad * wel) * 2 * sizeof(__nv_bfloat16);    // [conv][mode][hi|lo]
+  if (off + 2 * wel * sizeof(__nv_bfloat16) > wc.bytes) return nullptr;
+  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(wc.base + off);
+  __nv_bfloat16* lo = hi + wel;
+  const size_t key = ((size_t)cs.w_off / 4) * 2 + dgrad;
+  if (key >= wc.ok.size()) wc.ok.resize(key + 1, 0);
+  if (!wc.ok[key]) {
+    if (tc_pack_weights(c.params + cs.w_off, hi, lo, cs.cout, cs.cin, cs.k, dgrad, c.p->precision, c.st) != 0) return nullptr;
+    wc.ok[key] = 1;
+  }
+  out->hi = hi; out->lo = lo;
+  return out;
+}
+
 static bool conv_on_tc(const Ctx& c, const ConvSpec& cs, int Hin, int Win) {
   return c.p->tc && tc_conv_supported(cs.cin, cs.cout, cs.k, cs.stride, cs.pad, cs.dil, Hin, Win);
 }
@@ -262,7 +291,8 @@ static int conv_bn_forward(const Ctx& c, const ConvSpec& cs, const BnSpec& bs, c
   float* rm = c.buffers + bs.rm_off; float* rv = c.buffers + bs.rv_off;
   if (conv_on_tc(c, cs, cb.Hin, cb.Win)) {
     float* partial = c.training ? c.f(c.p->partial) : nullptr;
-    DDN_TRY(tc_conv_planes(c.planes(in_p), w, nullptr, raw, nullptr, partial, N, cb.Hin, cb.Win, cs.cin, cs.cout, cs.k, cs.stride,
+    TcPlanes wpk_s; const TcPlanes* wpk = cached_pack(c, cs, 0, &wpk_s);
+    DDN_TRY(tc_conv_planes(c.planes(in_p), w, wpk, raw, nullptr, partial, N, cb.Hin, cb.Win, cs.cin, cs.cout, cs.k, cs.stride,
                            cs.dil, 0, c.p->precision, c.ws + c.p->wws, tc_weight_ws_bytes(), c.st));
     if (c.training)
       return launch_bn_stats_finalize(partial, tc_bn_partial_blocks(N, cb.Hout, cb.Wout), M, bs.C, c.f(cb.mean), c.f(cb.invstd),
@@ -349,11 +379,12 @@ static int conv_backward(const Ctx& c, const ConvSpec& cs, const float* in, cons
     DDN_TRY(tc_wgrad_planes(c.planes(in_p), c.planes(p.grad_p), dw, N, Hin, Win, cs.cin, cs.cout, cs.k, cs.stride, cs.dil,
                             p.precision, c.f(p.dwp), c.st));
     if (dx) {
+      TcPlanes wpk_s; const TcPlanes* wpk = cached_pack(c, cs, 1, &wpk_s);
       if (cs.stride == 2)   // zero-insert the fp32 dY into the (now free) gradient planes, then an ordinary stride-1 dgrad
-        DDN_TRY(tc_dgrad_strided(dy, c.planes(p.grad_p), w, dx, addend, N, Hin, Win, cs.cin, cs.cout, cs.k, p.precision,
+        DDN_TRY(tc_dgrad_strided(dy, c.planes(p.grad_p), w, wpk, dx, addend, N, Hin, Win, cs.cin, cs.cout, cs.k, p.precision,
                                  c.ws + p.wws, tc_weight_ws_bytes(), c.st));
       else
-        DDN_TRY(tc_conv_planes(c.planes(p.grad_p), w, nullptr, dx, addend, nullptr, N, Hin, Win, cs.cin, cs.cout, cs.k, 1, cs.dil, 1,
+        DDN_TRY(tc_conv_planes(c.planes(p.grad_p), w, wpk, dx, addend, nullptr, N, Hin, Win, cs.cin, cs.cout, cs.k, 1, cs.dil, 1,
                                p.precision, c.ws + p.wws, tc_weight_ws_bytes(), c.st));
     }
     return 0;
@@ -498,6 +529,22 @@ extern "C" int ddn_resnet34_8s_buffer_table(ddn_tensor_entry* out, int cap) {
 }
 extern "C" int64_t ddn_resnet34_8s_param_count(int D) { return (D < 1 || D > 32) ? DDN_EINVAL : get_spec(D).n_params; }
 extern "C" int64_t ddn_resnet34_8s_buffer_count(void) { return get_spec(3).n_buffers; }
+
+extern "C" size_t ddn_resnet34_8s_weight_cache_bytes(int D) {
+  if (D < 1 || D > 32) return 0;
+  return (size_t)get_spec(D).n_params * 2 * 2 * sizeof(__nv_bfloat16) + 4096;
+}
+
+extern "C" int ddn_resnet34_8s_set_weight_cache(void* cache, size_t bytes, const float* params, uint64_t version, int precision) {
+  std::lock_guard<std::mutex> lk(g_wcache_mu);
+  WeightCache& wc = g_wcache;
+  const bool same = wc.base == (char*)cache && wc.bytes == bytes && wc.params == params && wc.version == version && wc.precision == precision;
+  if (!same) {
+    wc.base = (char*)cache; wc.bytes = bytes; wc.params = params; wc.version = version; wc.precision = precision;
+    std::fill(wc.ok.begin(), wc.ok.end(), 0);
+  }
+  return 0;
+}
 
 extern "C" size_t ddn_resnet34_8s_workspace_bytes(int B, int H, int W, int D, int training, int precision) {
   Plan p;

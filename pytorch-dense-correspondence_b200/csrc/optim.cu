@@ -1,0 +1,49 @@
+// Fused Adam over the flat parameter / gradient arrays.
+// Replaces torch.optim.Adam(lr, weight_decay) as constructed at dense_correspondence/training/training.py:133-145 and
+// stepped at :346 (one multi-kernel pass per parameter tensor in torch 1.1) with ONE HBM-bound launch:
+// read p, g, m, v + write p, m, v = 28 bytes per parameter (596 MB for Resnet34_8s: ~90 us at HBM speed).
+// Semantics = torch.optim.Adam (no amsgrad): L2 weight decay folded into the gradient, bias-corrected moments.
+#include "common.cuh"
+
+namespace ddn {
+
+__global__ void __launch_bounds__(256)
+adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n4,
+                 int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, float bc1, float bc2_sqrt,
+                 float grad_scale) {
+  const float step_size = lr / bc1;
+  auto upd = [&](float& pv, float gv, float& mv, float& vv) {
+    gv = fmaf(weight_decay, pv, gv * grad_scale);
+    mv = fmaf(beta1, mv, (1.f - beta1) * gv);
+    vv = fmaf(beta2, vv, (1.f - beta2) * gv * gv);
+    const float denom = sqrtf(vv) / bc2_sqrt + eps;
+    pv -= step_size * (mv / denom);
+  };
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    const float4 gv = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    upd(pv.x, gv.x, mv.x, vv.x); upd(pv.y, gv.y, mv.y, vv.y); upd(pv.z, gv.z, mv.z, vv.z); upd(pv.w, gv.w, mv.w, vv.w);
+    reinterpret_cast<float4*>(p)[i] = pv; reinterpret_cast<float4*>(m)[i] = mv; reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  const int64_t tail = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (blockIdx.x == 0 && tail < n) upd(p[tail], g[tail], m[tail], v[tail]);
+}
+
+}  // namespace ddn
+
+using namespace ddn;
+
+extern "C" int ddn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, int64_t step,
+                             float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale, void* stream) {
+  DDN_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && n > 0 && step >= 1, "adam: bad arguments");
+  DDN_CHECK_ARG(((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(exp_avg) |
+                  reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0, "adam: arrays must be 16-byte aligned");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const int64_t n4 = n >> 2;
+  const int blocks = (int)std::min<int64_t>(ceil_div(n4 + 1, 256), (int64_t)num_sms() * 8);
+  DDN_LAUNCH(adam_step_kernel, blocks, 256, 0, (cudaStream_t)stream, params, grads, exp_avg, exp_avg_sq, n4, n, lr, beta1, beta2,
+             eps, weight_decay, (float)bc1, (float)sqrt(bc2), grad_scale);
+  return 0;
+}

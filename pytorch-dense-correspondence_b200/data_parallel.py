@@ -47,6 +47,9 @@ def broadcast_parameters(module, src=0, group=None):
     with torch.no_grad():
         for t in list(module.parameters()) + list(module.buffers()):
             dist.broadcast(t.data, src=src, group=group)
+        for m in module.modules():         # writes through .data are invisible to autograd's version counters
+            if hasattr(m, "mark_parameters_changed"):
+                m.mark_parameters_changed()
 
 
 def _flat_view_of(tensors):

@@ -25,7 +25,8 @@ from . import _native as N
 _BN_MOMENTUM = 0.1   # nn.BatchNorm2d defaults, resnet.py:46
 _BN_EPS = 1e-5
 
-_default_precision = [N.PRECISION_FP32_SIMT]
+_cache_nonce = [0]
+_default_precision = [N.PRECISION_BF16X3]     # fp32-equivalent results on the tensor cores
 
 
 def set_default_precision(p):
@@ -52,6 +53,7 @@ class _Backbone(torch.autograd.Function):
         training = 1 if owner.training else 0
         keep = bool(training) and any(ctx.needs_input_grad)   # grad mode is off inside Function.forward; this is the signal
         prec = owner.precision
+        owner._register_weight_cache(flat, prec)
         ws_bytes = N.lib.ddn_resnet34_8s_workspace_bytes(B, H, W, D, training, prec)
         if ws_bytes == 0:
             raise N.DdnError("bad shape for Resnet34_8s: %s" % N.lib.ddn_last_error().decode())
@@ -78,10 +80,13 @@ class _Backbone(torch.autograd.Function):
         dy = dy.contiguous()
         N.require_cuda_f32(dy, "descriptor cotangent")
         flat, _ = owner._ensure_flat(dy.device)
+        owner._register_weight_cache(flat, ctx.prec)
         grads = torch.empty_like(flat)
         N.check(N.lib.ddn_resnet34_8s_backward(N.ptr(dy), N.ptr(flat), N.ptr(grads), N.ptr(ctx.ws), ctx.ws.numel(),
                                                B, H, W, D, _BN_EPS, ctx.prec, N.stream_ptr()))
         ctx.ws = None
+        if owner._pad_index is not None:           # alignment padding between tensors: keep it zero (it is all-reduced / stepped too)
+            grads.index_fill_(0, owner._pad_index.to(grads.device), 0.0)
         # Gradients are accumulated by THIS function into one flat array that every p.grad aliases (like a fused
         # "main_grad"): the second backward of a step (image B, then image A) is one flat add instead of 110 small
         # AccumulateGrad kernels, and the data-parallel all-reduce / a fused optimizer see a single buffer.
@@ -114,6 +119,13 @@ class Resnet34_8s(nn.Module):
         self._flat_bufs = torch.zeros(n_bufs, dtype=torch.float32)
         self._flat_version = 0
         self._flat_grad = None
+        pads = []
+        for (_, _, off, n) in self._ptab:
+            pads += list(range(off + n, (off + n + 3) // 4 * 4))
+        self._pad_index = torch.tensor(pads, dtype=torch.long) if pads else None
+        self._wcache = None
+        self._wcache_nonce = 0
+        self._param_epoch = 0
         self._params = []
         self._nbt = []
         root = _Holder()
@@ -211,6 +223,25 @@ class Resnet34_8s(nn.Module):
         else:
             self._flat = self._flat.to(dev)   # CPU copy only serves state_dict round trips
         return out
+
+    def _register_weight_cache(self, flat, prec):
+        """Packed bf16 weights are cached across the calls of a step and re-packed when the parameters change (the
+        tensor version counter of the flat array advances on every in-place update of it or of any view)."""
+        if prec == N.PRECISION_FP32_SIMT:
+            return
+        if self._wcache is None or self._wcache.device != flat.device:
+            self._wcache = torch.empty(N.lib.ddn_resnet34_8s_weight_cache_bytes(self.num_classes), dtype=torch.uint8,
+                                       device=flat.device)
+            _cache_nonce[0] += 1           # a fresh buffer may reuse the address of a dead one: never look "unchanged"
+            self._wcache_nonce = _cache_nonce[0]
+        # p.data = view shares storage but NOT the autograd version counter with the flat array, so the key is the sum of the
+        # parameters' own counters (every optimizer / load_state_dict / init write advances one of them) plus manual bumps
+        version = (self._wcache_nonce << 44) + ((self._flat_version + self._param_epoch) << 32) + (sum(p._version for p in self._params) & 0xffffffff)
+        N.check(N.lib.ddn_resnet34_8s_set_weight_cache(N.ptr(self._wcache), self._wcache.numel(), N.ptr(flat), version, prec))
+
+    def mark_parameters_changed(self):
+        """Call after writing parameters through a raw pointer / ``.data`` (anything autograd's version counters miss)."""
+        self._param_epoch += 1
 
     @property
     def flat_gradient(self):

@@ -214,11 +214,14 @@ def test_single_image_inference_and_state_dict_roundtrip(tmp_path):
     (tmp_path / "training.yaml").write_text(yaml.safe_dump({"dense_correspondence_network": cfg}))
     dcn2 = pdc_b200.DenseCorrespondenceNetwork.from_model_folder(str(tmp_path))
     dcn2.eval()
+    assert rel(dcn2.forward_single_image_tensor(x), res) < 1e-3          # default arithmetic: bf16x3 on the tensor cores
+    dcn2.fcn.precision = N.PRECISION_FP32_SIMT
     assert torch.equal(dcn2.forward_single_image_tensor(x), res)
     # a reference-style checkpoint (keys without the _fcn. prefix) loads through the fallback of net.py:429-433
     torch.save(oracle.state_dict(), tmp_path / "000002.pth")
     dcn3 = pdc_b200.DenseCorrespondenceNetwork.from_model_folder(str(tmp_path), iteration=2)
     dcn3.eval()
+    dcn3.fcn.precision = N.PRECISION_FP32_SIMT
     assert torch.equal(dcn3.forward_single_image_tensor(x), res)
 
 
@@ -236,3 +239,60 @@ def test_contract_errors_on_gpu():
     y = net(torch.zeros(1, 3, 64, 64, device=DEV).requires_grad_())
     with pytest.raises(RuntimeError):
         y.sum().backward()                                           # eval-mode forward keeps nothing
+
+
+def test_fused_adam_matches_torch_adam():
+    """ddn_adam_step vs torch.optim.Adam(lr=1e-4, weight_decay=1e-4) (training.py:133-145) over 3 steps with a decaying lr."""
+    D = 3
+    net_a, _ = make_net(D)
+    net_b, _ = make_net(D)
+    ref = torch.optim.Adam(net_a.parameters(), lr=1e-4, weight_decay=1e-4)
+    ours = pdc_b200.FusedAdam(net_b, lr=1e-4, weight_decay=1e-4)
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(1, 3, 64, 96, generator=gen).to(DEV); cot = torch.randn(1, D, 64, 96, generator=gen).to(DEV)
+    for it in range(3):
+        for opt, net in ((ref, net_a), (ours, net_b)):
+            opt.zero_grad()
+            (net(x) * cot).sum().backward()
+            opt.param_groups[0]["lr"] = 1e-4 * (0.9 ** it)
+        # identical gradients by construction: copy so that only the optimizer arithmetic is compared
+        net_b.flat_gradient.copy_(net_a.flat_gradient)
+        ref.step(); ours.step()
+        a, b = net_a.flat_parameters, net_b.flat_parameters
+        assert float((a - b).abs().max()) <= 2e-7 + 1e-6 * float(a.abs().max()), it
+    sd = ours.state_dict()
+    assert sd["step"] == 3 and sd["exp_avg"].shape == net_b.flat_parameters.shape
+
+
+def test_weight_pack_cache_follows_parameter_updates():
+    """The tensor-core weight packs are cached across calls; any parameter write (optimizer, load_state_dict, FusedAdam,
+    a second module reusing freed addresses) must invalidate them."""
+    D = 3
+    x = torch.randn(1, 3, 64, 96, generator=torch.Generator().manual_seed(8)).to(DEV)
+    net, oracle = make_net(D, "bf16x3")
+    net.eval(); oracle.eval()
+    with torch.no_grad():
+        y0 = net(x).clone()
+        assert rel(y0, oracle(x.cpu())) < 1e-3
+        assert torch.equal(net(x), y0)                       # cached packs, same result
+        for p in net.parameters():                           # in-place update through the views (what optimizers do)
+            p.mul_(1.01)
+        for p in oracle.parameters():
+            p.mul_(1.01)
+        y1 = net(x)
+        assert rel(y1, oracle(x.cpu())) < 1e-3 and not torch.equal(y1, y0)
+    del net
+    net2, oracle2 = make_net(D, "bf16x3")                    # new module, very likely the same device addresses
+    net2.eval(); oracle2.eval()
+    with torch.no_grad():
+        assert rel(net2(x), oracle2(x.cpu())) < 1e-3
+    opt = pdc_b200.FusedAdam(net2, lr=1e-2)
+    net2.train()
+    (net2(x) ** 2).sum().backward()
+    opt.step()                                               # raw-pointer write
+    net2.eval()
+    with torch.no_grad():
+        ya = net2(x)
+        net2.precision = N.PRECISION_FP32_SIMT               # the fp32 path never uses the cache: must agree
+        yb = net2(x)
+    assert rel(ya, yb) < 1e-3
