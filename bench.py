@@ -310,9 +310,9 @@ def run_ours(args):
         mma_per_mac = {"fp32": 0, "bf16x3": 3, "bf16": 1}[prec_name]
         roof = {"bound": "tensor", "kernel": dom, "achieved": a, "peak": tf_peak, "unit": "TFLOP/s", "frac": a / tf_peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel class (the 512->512 dilation-4 conv
-                # at B=8; algorithmic 167 MB) from the committed `ncu --set full` capture profiles/r1_prof_conv_tc_r1g.md
+                # at B=8; algorithmic 167 MB) from the committed `ncu --set full` capture profiles/r1_prof_conv_tc_final.md
                 "traffic": 130.6e6 if (prec_name == "bf16x3" and Bp == 8 and H == 480 and W == 640) else None,
-                "traffic_source": "profiles/r1_prof_conv_tc_r1g.md (largest launch of the class, bytes)",
+                "traffic_source": "profiles/r1_prof_conv_tc_final.md (largest launch of the class, bytes)",
                 "issued_tensor_TFLOPs": a * mma_per_mac, "issued_frac": a * mma_per_mac / tf_peak,
                 "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a long step)",
                 "launches": prof[dom]["launches"], "avg_launch_ms": prof[dom]["ms"] / max(1, prof[dom]["launches"]),
