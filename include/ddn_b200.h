@@ -218,6 +218,15 @@ int ddn_upsample_bilinear_backward(const float* dy, float* dx, int NC, int h, in
 /* Data-parallel helpers on the flat gradient: g *= scale (after an all-reduce SUM over ranks). */
 int ddn_scale_inplace(float* g, int64_t n, float scale, void* stream);
 
+/* Batched best-match search: for each of Q query descriptors [Q,D] find the pixel of the descriptor image res_b
+ * (element (p, c) at p*stride_p + c*stride_c, p = u + W*v) with the smallest L2 distance -- the device-side equivalent of
+ * DenseCorrespondenceNetwork.find_best_match (dense_correspondence/network/dense_correspondence_network.py:488-525), first
+ * minimum on ties like numpy.argmin.  best_uv [Q,2] int64 = (u, v), best_diff [Q] = that distance; norm_diffs (optional)
+ * [Q, H*W] = the full distance maps.  scratch: Q x 8 bytes. */
+int ddn_find_best_match(const float* res_b, int64_t stride_p, int64_t stride_c, int H, int W, int D,
+                        const float* queries, int Q, int64_t* best_uv, float* best_diff, float* norm_diffs,
+                        void* scratch, void* stream);
+
 /* Fused Adam step over flat arrays == torch.optim.Adam(lr, betas, eps, weight_decay) as used by
  * dense_correspondence/training/training.py:133-145,346 (L2 weight decay folded into the gradient, bias-corrected moments,
  * no amsgrad).  `step` is the 1-based step count; grads are read as grads[i]*grad_scale (1/world after a SUM all-reduce). */

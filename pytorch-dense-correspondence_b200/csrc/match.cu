@@ -1,0 +1,89 @@
+// Batched best-match search in descriptor space.
+// Replaces the host-side numpy scan of DenseCorrespondenceNetwork.find_best_match
+// (dense_correspondence/network/dense_correspondence_network.py:488-525: norm_diffs = sqrt(sum((res_b - d)^2, axis=2));
+// argmin; called ~100x per image pair by evaluation.py:993,1047 after a D2H copy of both descriptor images) with one
+// launch for Q query descriptors against a descriptor image that stays on the device.
+// HBM/L2-bound: every query streams the [P, D] image once (1.23*D MB); queries of one launch share it through L2.
+#include "common.cuh"
+
+namespace ddn {
+
+constexpr int MATCH_THREADS = 256;
+constexpr int MATCH_MAXD = 32;
+
+// res_b element (p, c) at p*sp + c*sc.  best[q] = packed (float bits of squared distance << 32 | pixel index), pre-set to ~0.
+// Squared distances are non-negative, so their IEEE bit patterns order like the values; equal distances resolve to the
+// smallest pixel index, which is numpy.argmin's first-minimum rule.
+__global__ void __launch_bounds__(MATCH_THREADS)
+best_match_kernel(const float* __restrict__ res_b, int64_t sp, int64_t sc, int64_t P, int D,
+                  const float* __restrict__ queries, int Q, int pixels_per_block,
+                  unsigned long long* __restrict__ best, float* __restrict__ norm_diffs) {
+  const int q = blockIdx.y;
+  __shared__ float qd[MATCH_MAXD];
+  if (threadIdx.x < D) qd[threadIdx.x] = queries[(int64_t)q * D + threadIdx.x];
+  __syncthreads();
+  const int64_t p0 = (int64_t)blockIdx.x * pixels_per_block;
+  const int64_t p1 = min(P, p0 + pixels_per_block);
+  unsigned long long loc = ~0ull;
+  for (int64_t p = p0 + threadIdx.x; p < p1; p += MATCH_THREADS) {
+    float s = 0.f;
+    for (int c = 0; c < D; ++c) {
+      float d = __ldg(res_b + p * sp + c * sc) - qd[c];
+      s = fmaf(d, d, s);
+    }
+    if (norm_diffs) norm_diffs[(int64_t)q * P + p] = sqrtf(s);
+    unsigned long long key = ((unsigned long long)__float_as_uint(s) << 32) | (unsigned long long)(uint32_t)p;
+    loc = key < loc ? key : loc;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long other = __shfl_xor_sync(0xffffffffu, loc, o);
+    loc = other < loc ? other : loc;
+  }
+  __shared__ unsigned long long sm[MATCH_THREADS / 32];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = loc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    loc = threadIdx.x < MATCH_THREADS / 32 ? sm[threadIdx.x] : ~0ull;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      unsigned long long other = __shfl_xor_sync(0xffffffffu, loc, o);
+      loc = other < loc ? other : loc;
+    }
+    if (threadIdx.x == 0) atomicMin(best + q, loc);
+  }
+}
+
+__global__ void best_match_finish_kernel(const unsigned long long* __restrict__ best, int Q, int W,
+                                         int64_t* __restrict__ uv, float* __restrict__ diff) {
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  unsigned long long k = best[q];
+  uint32_t p = (uint32_t)(k & 0xffffffffull);
+  uv[2 * q + 0] = p % W;            // u = column
+  uv[2 * q + 1] = p / W;            // v = row
+  diff[q] = sqrtf(__uint_as_float((uint32_t)(k >> 32)));
+}
+
+}  // namespace ddn
+
+using namespace ddn;
+
+extern "C" int ddn_find_best_match(const float* res_b, int64_t stride_p, int64_t stride_c, int H, int W, int D,
+                                   const float* queries, int Q, int64_t* best_uv, float* best_diff, float* norm_diffs,
+                                   void* scratch /* Q x 8 bytes */, void* stream) {
+  DDN_CHECK_ARG(res_b && queries && best_uv && best_diff && scratch, "null argument");
+  DDN_CHECK_ARG(H > 0 && W > 0 && D >= 1 && D <= MATCH_MAXD && Q >= 1 && Q <= 65535 && (int64_t)H * W < (1ll << 32), "bad sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t P = (int64_t)H * W;
+  DDN_CUDA(cudaMemsetAsync(scratch, 0xff, sizeof(unsigned long long) * Q, st));
+  int blocks_x = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(P, 2048), ceil_div((int64_t)num_sms() * 4, Q)));
+  int ppb = (int)(ceil_div(ceil_div(P, blocks_x), MATCH_THREADS) * MATCH_THREADS);
+  blocks_x = (int)ceil_div(P, ppb);
+  dim3 grid(blocks_x, Q);
+  DDN_LAUNCH(best_match_kernel, grid, MATCH_THREADS, 0, st, res_b, stride_p, stride_c, P, D, queries, Q, ppb,
+             reinterpret_cast<unsigned long long*>(scratch), norm_diffs);
+  DDN_LAUNCH(best_match_finish_kernel, (Q + 127) / 128, 128, 0, st, reinterpret_cast<const unsigned long long*>(scratch), Q, W,
+             best_uv, best_diff);
+  return 0;
+}

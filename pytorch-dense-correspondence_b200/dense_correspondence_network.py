@@ -218,6 +218,28 @@ class DenseCorrespondenceNetwork(nn.Module):
         return best_match_uv, best_match_diff, norm_diffs
 
     @staticmethod
+    def find_best_matches_cuda(pixels_a, res_a, res_b, return_norm_diffs=False):
+        """Device-side, batched ``find_best_match`` (net.py:488-525): ``pixels_a`` [Q,2] (u,v) integer pixels in image A,
+        ``res_a`` / ``res_b`` [H,W,D] float32 CUDA descriptor images (what ``forward_single_image_tensor`` returns, any
+        strides).  -> (best_uv [Q,2] int64 CUDA, best_diff [Q] float32 CUDA[, norm_diffs [Q,H,W]]) without leaving the
+        GPU; evaluation.py:993,1047 does this 100x per pair on the host after a D2H copy."""
+        from . import _native as N
+        N.require_cuda_f32(res_a, "res_a", contiguous=False); N.require_cuda_f32(res_b, "res_b", contiguous=False)
+        H, W, D = res_b.shape
+        if res_b.stride(0) != W * res_b.stride(1):
+            res_b = res_b.contiguous()
+        px = torch.as_tensor(pixels_a, dtype=torch.long, device=res_a.device).reshape(-1, 2)
+        q = res_a[px[:, 1], px[:, 0]].contiguous()                      # [Q, D] query descriptors
+        Q = q.shape[0]
+        uv = torch.empty(Q, 2, dtype=torch.int64, device=res_b.device)
+        diff = torch.empty(Q, dtype=torch.float32, device=res_b.device)
+        nd = torch.empty(Q, H, W, dtype=torch.float32, device=res_b.device) if return_norm_diffs else None
+        scratch = torch.empty(Q, dtype=torch.int64, device=res_b.device)
+        N.check(N.lib.ddn_find_best_match(N.ptr(res_b), res_b.stride(1), res_b.stride(2), H, W, D, N.ptr(q), Q, N.ptr(uv),
+                                          N.ptr(diff), N.ptr(nd), N.ptr(scratch), N.stream_ptr()))
+        return (uv, diff, nd) if return_norm_diffs else (uv, diff)
+
+    @staticmethod
     def find_best_match_for_descriptor(descriptor, res):
         norm_diffs = np.sqrt(np.sum(np.square(res - descriptor), axis=2))
         best_match_flattened_idx = np.argmin(norm_diffs)

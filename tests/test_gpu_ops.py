@@ -273,3 +273,27 @@ def test_host_buffer_entry_point(golden_dir):
                                           len(idx[2]), p(idx[4]), p(idx[5]), len(idx[4]), 0.5, 0.5, 1.0, 1.0, 1, p(five))
     N.check(rc)
     np.testing.assert_allclose(five[:4], g["five"][:4], rtol=2e-6, atol=1e-7)
+
+
+def test_find_best_matches_cuda_vs_numpy_reference():
+    """Batched device-side best match vs the reference's numpy scan (net.py:488-525), on the strided [H,W,D] view that
+    forward_single_image_tensor returns; includes an exact tie (first minimum wins, like numpy.argmin)."""
+    H, W, D, Q = 120, 160, 3, 37
+    gen = torch.Generator().manual_seed(12)
+    a = torch.randn(1, D, H, W, generator=gen); b = torch.randn(1, D, H, W, generator=gen)
+    b[0, :, 50, 60] = b[0, :, 10, 20]                                  # duplicate descriptor -> tie
+    res_a = a[0].permute(1, 2, 0); res_b = b[0].permute(1, 2, 0)        # strided views, like the network output
+    px = torch.stack([torch.randint(0, W, (Q,), generator=gen), torch.randint(0, H, (Q,), generator=gen)], 1)
+    with torch.no_grad():
+        a[0, :, px[0, 1], px[0, 0]] = b[0, :, 10, 20]                   # query 0 matches the duplicated pixel exactly
+    uv, diff, nd = pdc_b200.DenseCorrespondenceNetwork.find_best_matches_cuda(px, res_a.to(DEV), res_b.to(DEV), return_norm_diffs=True)
+    ra, rb = res_a.numpy(), res_b.numpy()
+    for i in range(Q):
+        ref_uv, ref_diff, ref_nd = pdc_b200.DenseCorrespondenceNetwork.find_best_match((int(px[i, 0]), int(px[i, 1])), ra, rb)
+        got_uv = (int(uv[i, 0]), int(uv[i, 1]))
+        if got_uv != ref_uv:        # only allowed when the two candidates are numerically tied
+            assert abs(ref_nd[got_uv[1], got_uv[0]] - ref_diff) < 1e-6, (i, got_uv, ref_uv)
+        assert abs(float(diff[i]) - float(ref_diff)) < 1e-5
+        if i < 3:
+            np.testing.assert_allclose(nd[i].cpu().numpy(), ref_nd, rtol=1e-5, atol=1e-6)
+    assert (int(uv[0, 0]), int(uv[0, 1])) == (20, 10) and float(diff[0]) == 0.0     # first of the two exact matches
