@@ -42,9 +42,18 @@ static inline int64_t bn_rows_per_block(int64_t M, int C) {
 
 // column sums of v0(x) and v1(x) over a row chunk -> partial[0][blk][C], partial[1][blk][C]
 // MODE 0: (x, x^2)      MODE 1: (g, g*xhat) with g = dy * (y > 0 if relu)
+// 4 packed bf16 values > 0 ?  (sign bit clear and not +/-0)
+__device__ __forceinline__ void mask_from_bf16x4(uint2 h, float4& g) {
+  if ((h.x & 0x8000u) || !(h.x & 0x7fffu)) g.x = 0.f;
+  if ((h.x & 0x80000000u) || !(h.x & 0x7fff0000u)) g.y = 0.f;
+  if ((h.y & 0x8000u) || !(h.y & 0x7fffu)) g.z = 0.f;
+  if ((h.y & 0x80000000u) || !(h.y & 0x7fff0000u)) g.w = 0.f;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(BN_THREADS)
 bn_colsum_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ y,
+                 const __nv_bfloat16* __restrict__ y_hi,
                  const float* __restrict__ mean, const float* __restrict__ invstd,
                  int64_t M, int C, int64_t rows_per_block, int relu, float* __restrict__ partial) {
   const int q = C >> 2;
@@ -65,8 +74,12 @@ bn_colsum_kernel(const float* __restrict__ x, const float* __restrict__ dy, cons
     } else {
       float4 g = __ldg(reinterpret_cast<const float4*>(dy + r * C) + cq);
       if (relu) {
-        float4 o = __ldg(reinterpret_cast<const float4*>(y + r * C) + cq);
-        g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+        if (y_hi) {     // the bf16 "hi" plane of y has y's sign and zero-ness: half the bytes of the fp32 copy
+          mask_from_bf16x4(__ldg(reinterpret_cast<const uint2*>(y_hi + r * C) + cq), g);
+        } else {
+          float4 o = __ldg(reinterpret_cast<const float4*>(y + r * C) + cq);
+          g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+        }
       }
       s0.x += g.x; s0.y += g.y; s0.z += g.z; s0.w += g.w;
       s1.x = fmaf(g.x, (v.x - mu.x) * is.x, s1.x); s1.y = fmaf(g.y, (v.y - mu.y) * is.y, s1.y);
@@ -88,31 +101,35 @@ bn_colsum_kernel(const float* __restrict__ x, const float* __restrict__ dy, cons
   }
 }
 
-// Column sums of the per-block partials in fp64.  Block = 8 channels (one 32-byte sector per partial row) x 32 slices;
-// every thread walks nblk/32 rows with 4 independent loads in flight, so the chain is a few iterations long even for
-// ~1200 partial rows (the previous 8-slice version spent 40-50 us per call in load latency on 2-16 CTAs).
+// Column sums of the per-block partials in fp64.  Block = 4 channels (one 16-byte segment per partial row) x 64 slices;
+// every thread walks nblk/64 rows with 8 independent loads in flight, so even ~1200 partial rows are ~5 dependent rounds
+// (these kernels are pure load latency: 2-128 CTAs, a few KB to a few MB of partials).
+constexpr int FIN_CH = 4, FIN_SLICES = 64;
 __device__ __forceinline__ void reduce_partials(const float* __restrict__ partial, int nblk, int C, int c, int slice,
                                                 double& s, double& ss) {
-  double s0 = 0, s1 = 0, q0 = 0, q1 = 0;
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0, q0 = 0, q1 = 0, q2 = 0, q3 = 0;
   if (c < C) {
     const float* ps = partial + c;
     const float* pq = partial + (int64_t)nblk * C + c;
     int b = slice;
-    for (; b + 32 < nblk; b += 64) {
-      float a0 = __ldg(ps + (int64_t)b * C), a1 = __ldg(ps + (int64_t)(b + 32) * C);
-      float b0 = __ldg(pq + (int64_t)b * C), b1 = __ldg(pq + (int64_t)(b + 32) * C);
-      s0 += (double)a0; s1 += (double)a1; q0 += (double)b0; q1 += (double)b1;
+    for (; b + 3 * FIN_SLICES < nblk; b += 4 * FIN_SLICES) {
+      float a0 = __ldg(ps + (int64_t)b * C), a1 = __ldg(ps + (int64_t)(b + FIN_SLICES) * C);
+      float a2 = __ldg(ps + (int64_t)(b + 2 * FIN_SLICES) * C), a3 = __ldg(ps + (int64_t)(b + 3 * FIN_SLICES) * C);
+      float b0 = __ldg(pq + (int64_t)b * C), b1 = __ldg(pq + (int64_t)(b + FIN_SLICES) * C);
+      float b2 = __ldg(pq + (int64_t)(b + 2 * FIN_SLICES) * C), b3 = __ldg(pq + (int64_t)(b + 3 * FIN_SLICES) * C);
+      s0 += (double)a0; s1 += (double)a1; s2 += (double)a2; s3 += (double)a3;
+      q0 += (double)b0; q1 += (double)b1; q2 += (double)b2; q3 += (double)b3;
     }
-    if (b < nblk) { s0 += (double)__ldg(ps + (int64_t)b * C); q0 += (double)__ldg(pq + (int64_t)b * C); }
+    for (; b < nblk; b += FIN_SLICES) { s0 += (double)__ldg(ps + (int64_t)b * C); q0 += (double)__ldg(pq + (int64_t)b * C); }
   }
-  s = s0 + s1; ss = q0 + q1;
-  __shared__ double sh[2][32][8];
-  const int ch = threadIdx.x & 7;
+  s = (s0 + s1) + (s2 + s3); ss = (q0 + q1) + (q2 + q3);
+  __shared__ double sh[2][FIN_SLICES][FIN_CH];
+  const int ch = threadIdx.x & (FIN_CH - 1);
   sh[0][slice][ch] = s; sh[1][slice][ch] = ss;
   __syncthreads();
   if (slice == 0) {
 #pragma unroll 8
-    for (int k = 1; k < 32; ++k) { s += sh[0][k][ch]; ss += sh[1][k][ch]; }
+    for (int k = 1; k < FIN_SLICES; ++k) { s += sh[0][k][ch]; ss += sh[1][k][ch]; }
   }
 }
 
@@ -121,7 +138,7 @@ bn_stats_finalize_kernel(const float* __restrict__ partial, int nblk, int64_t M,
                          float* __restrict__ mean, float* __restrict__ invstd,
                          float* __restrict__ running_mean, float* __restrict__ running_var,
                          float momentum, float eps) {
-  const int c = blockIdx.x * 8 + (threadIdx.x & 7), slice = threadIdx.x >> 3;
+  const int c = blockIdx.x * FIN_CH + (threadIdx.x & (FIN_CH - 1)), slice = threadIdx.x / FIN_CH;
   double s, ss;
   reduce_partials(partial, nblk, C, c, slice, s, ss);
   if (slice != 0 || c >= C) return;
@@ -180,7 +197,7 @@ bn_apply_kernel(BnApplyArgs a) {
 __global__ void __launch_bounds__(256)
 bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C,
                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int c = blockIdx.x * 8 + (threadIdx.x & 7), slice = threadIdx.x >> 3;
+  const int c = blockIdx.x * FIN_CH + (threadIdx.x & (FIN_CH - 1)), slice = threadIdx.x / FIN_CH;
   double s, ss;
   reduce_partials(partial, nblk, C, c, slice, s, ss);
   if (slice != 0 || c >= C) return;
@@ -206,8 +223,12 @@ bn_bwd_apply_kernel(BnBwdArgs a) {
     int c = (int)(i % q) << 2;
     float4 g = __ldg(reinterpret_cast<const float4*>(a.dy) + i);
     if (a.relu) {
-      float4 o = __ldg(reinterpret_cast<const float4*>(a.y) + i);
-      g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+      if (a.y_hi) {
+        mask_from_bf16x4(__ldg(reinterpret_cast<const uint2*>(a.y_hi) + i), g);
+      } else {
+        float4 o = __ldg(reinterpret_cast<const float4*>(a.y) + i);
+        g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+      }
     }
     if (a.g_out) reinterpret_cast<float4*>(a.g_out)[i] = g;
     float4 v = __ldg(reinterpret_cast<const float4*>(a.x) + i);
@@ -320,16 +341,16 @@ int launch_bn_stats(const float* x, int64_t M, int C, float* partial, float* mea
                     float* running_mean, float* running_var, float momentum, float eps, cudaStream_t st) {
   DDN_TRY(check_c(C));
   int nblk = bn_partial_blocks(M, C);
-  DDN_LAUNCH(bn_colsum_kernel<0>, nblk, BN_THREADS, 0, st, x, nullptr, nullptr, nullptr, nullptr, M, C,
+  DDN_LAUNCH(bn_colsum_kernel<0>, nblk, BN_THREADS, 0, st, x, nullptr, nullptr, nullptr, nullptr, nullptr, M, C,
              bn_rows_per_block(M, C), 0, partial);
-  DDN_LAUNCH(bn_stats_finalize_kernel, (int)ceil_div(C, 8), 256, 0, st, partial, nblk, M, C, mean, invstd,
+  DDN_LAUNCH(bn_stats_finalize_kernel, (int)ceil_div(C, FIN_CH), 256, 0, st, partial, nblk, M, C, mean, invstd,
              running_mean, running_var, momentum, eps);
   return 0;
 }
 
 int launch_bn_stats_finalize(const float* partial, int nblk, int64_t M, int C, float* mean, float* invstd,
                              float* running_mean, float* running_var, float momentum, float eps, cudaStream_t st) {
-  DDN_LAUNCH(bn_stats_finalize_kernel, (int)ceil_div(C, 8), 256, 0, st, partial, nblk, M, C, mean, invstd,
+  DDN_LAUNCH(bn_stats_finalize_kernel, (int)ceil_div(C, FIN_CH), 256, 0, st, partial, nblk, M, C, mean, invstd,
              running_mean, running_var, momentum, eps);
   return 0;
 }
@@ -348,9 +369,9 @@ int launch_bn_apply(const BnApplyArgs& a, cudaStream_t st) {
 int launch_bn_backward(const BnBwdArgs& a, cudaStream_t st) {
   DDN_TRY(check_c(a.C));
   int nblk = bn_partial_blocks(a.M, a.C);
-  DDN_LAUNCH(bn_colsum_kernel<1>, nblk, BN_THREADS, 0, st, a.x, a.dy, a.y, a.mean, a.invstd, a.M, a.C,
+  DDN_LAUNCH(bn_colsum_kernel<1>, nblk, BN_THREADS, 0, st, a.x, a.dy, a.y, a.y_hi, a.mean, a.invstd, a.M, a.C,
              bn_rows_per_block(a.M, a.C), a.relu, a.partial);
-  DDN_LAUNCH(bn_bwd_finalize_kernel, (int)ceil_div(a.C, 8), 256, 0, st, a.partial, nblk, a.C, a.dgamma, a.dbeta);
+  DDN_LAUNCH(bn_bwd_finalize_kernel, (int)ceil_div(a.C, FIN_CH), 256, 0, st, a.partial, nblk, a.C, a.dgamma, a.dbeta);
   DDN_LAUNCH(bn_bwd_apply_kernel, ew_blocks(a.M * (a.C / 4)), BN_THREADS, 5 * a.C * sizeof(float), st, a);
   return 0;
 }

@@ -44,6 +44,7 @@ struct BnBwdArgs {
   const float* dy; const float* y; const float* x; const float* mean; const float* invstd; const float* gamma;
   float* dx; float* dgamma; float* dbeta; float* g_out; float* partial; int64_t M; int C; int relu; int training;
   __nv_bfloat16* dx_hi; __nv_bfloat16* dx_lo;   // optional: emit dx as bf16 hi/lo planes (dx itself may then be null)
+  const __nv_bfloat16* y_hi;                    // optional: bf16 hi plane of y, read for the ReLU mask instead of y
 };
 int launch_bn_backward(const BnBwdArgs& a, cudaStream_t st);
 

@@ -438,12 +438,14 @@ static int net_backward(const Ctx& c, const float* dy) {
     // out = relu(bn2(raw2) + residual):  g = dOut*(out>0) -> S[t2];  d raw2 -> planes (tensor core) or S[t1] (fp32)
     BnBwdArgs k2 = {S[cur], c.f(bb.out), c.f(bb.c2.raw), c.f(bb.c2.mean), c.f(bb.c2.invstd), c.params + b.b2.g_off,
                     nullptr, c.grads + b.b2.g_off, c.grads + b.b2.b_off, S[t2], c.f(p.partial), M1, b.b2.C, 1, 1, nullptr, nullptr};
+    if (p.tc) k2.y_hi = c.h(bb.out_p.hi);
     DDN_TRY(bn_backward_for(c, k2, b.c2, bb.c2.Hin, bb.c2.Win, S[t1]));
     // conv2: dW, d act1 -> S[t3]
     DDN_TRY(conv_backward(c, b.c2, c.f(bb.act1), bb.act1_p, S[t1], S[t3], nullptr, B, bb.c2.Hin, bb.c2.Win, bb.c2.Hout, bb.c2.Wout, b.c2.cin));
     // act1 = relu(bn1(raw1)): d raw1
     BnBwdArgs k1 = {S[t3], c.f(bb.act1), c.f(bb.c1.raw), c.f(bb.c1.mean), c.f(bb.c1.invstd), c.params + b.b1.g_off,
                     nullptr, c.grads + b.b1.g_off, c.grads + b.b1.b_off, nullptr, c.f(p.partial), M1, b.b1.C, 1, 1, nullptr, nullptr};
+    if (p.tc) k1.y_hi = c.h(bb.act1_p.hi);
     if (!b.has_ds) {
       DDN_TRY(bn_backward_for(c, k1, b.c1, bb.c1.Hin, bb.c1.Win, S[t1]));
       // dX = dgrad(conv1) + g
