@@ -227,6 +227,17 @@ int ddn_find_best_match(const float* res_b, int64_t stride_p, int64_t stride_c, 
                         const float* queries, int Q, int64_t* best_uv, float* best_diff, float* norm_diffs,
                         void* scratch, void* stream);
 
+/* Non-match sampling on the device: out_b[j] = flat index (u + W*v) of a pixel drawn uniformly from the nonzero pixels of
+ * `mask` [H*W] fp32 (nz[floor(rand_u[j] * #nonzero)], nonzero pixels in ascending order) or, when mask is NULL or empty,
+ * from the whole image (floor(rand_u*W), floor(rand_v*H)); out_a[j] = matches_a[j / non_matches_per_match] (may be NULL).
+ * == create_non_correspondences (dense_correspondence/correspondence_tools/correspondence_finder.py:276-405, whose
+ * "too close" perturbation is a no-op upstream) + create_non_matches / flatten_uv_tensor
+ * (dense_correspondence/dataset/spartan_dataset_masked.py:841-858,1255-1264), given the same uniform numbers. */
+size_t ddn_sample_non_matches_scratch_bytes(int H, int W);
+int ddn_sample_non_matches(const float* mask, int H, int W, const float* rand_u, const float* rand_v, int64_t n,
+                           const int64_t* matches_a, int64_t non_matches_per_match, int64_t* out_a, int64_t* out_b,
+                           void* scratch, size_t scratch_bytes, void* stream);
+
 /* Fused Adam step over flat arrays == torch.optim.Adam(lr, betas, eps, weight_decay) as used by
  * dense_correspondence/training/training.py:133-145,346 (L2 weight decay folded into the gradient, bias-corrected moments,
  * no amsgrad).  `step` is the 1-based step count; grads are read as grads[i]*grad_scale (1/world after a SUM all-reduce). */

@@ -351,3 +351,31 @@ def np_within_scene_loss(A, B, idx, cfg, W):
     non_match = (Sm + Sb) / scale
     loss = cfg["match_loss_weight"] * match + cfg["non_match_loss_weight"] * non_match
     return (loss, match) + terms, (hm, hb, hx)
+
+
+# ----------------------------------------------------------------------------- non-match sampling
+def create_non_correspondences_flat(matches_a_flat, image_shape, num_non_matches_per_match, img_b_mask, rand_u, rand_v):
+    """Restatement of create_non_correspondences (correspondence_tools/correspondence_finder.py:276-405) followed by
+    create_non_matches (dataset/spartan_dataset_masked.py:841-858) and flatten_uv_tensor (:1255-1264), with the uniform
+    random numbers passed in (the reference draws them with torch.rand).  The "too close" perturbation is omitted because it
+    is a no-op upstream: ``ones = torch.zeros_like(...)`` at correspondence_finder.py:354 keeps need_to_be_perturbed zero.
+    -> (non_matches_a, non_matches_b) int64 flat indices."""
+    H, W = image_shape
+    n = len(matches_a_flat) * num_non_matches_per_match
+
+    def rand_select_pixel():      # pytorch_rand_select_pixel, correspondence_finder.py:64-75
+        return torch.floor(rand_u[:n] * W).long(), torch.floor(rand_v[:n] * H).long()
+
+    if img_b_mask is not None:
+        nz = torch.nonzero(img_b_mask.view(-1, 1).squeeze(1))
+        if len(nz) == 0:
+            u, v = rand_select_pixel()
+        else:
+            idx = torch.floor(rand_u[:n] * len(nz)).long()
+            sel = torch.index_select(nz, 0, idx).squeeze(1)
+            u, v = sel % W, sel // W
+    else:
+        u, v = rand_select_pixel()
+    non_matches_b = v * W + u
+    non_matches_a = torch.t(matches_a_flat.repeat(num_non_matches_per_match, 1)).contiguous().view(-1)
+    return non_matches_a, non_matches_b

@@ -13,7 +13,7 @@ from .pixelwise_contrastive_loss import PixelwiseContrastiveLoss
 from . import loss_composer
 from .loss_composer import SpartanDatasetDataType
 from .fused_adam import FusedAdam
-from . import ops, synthetic, data_parallel
+from . import ops, synthetic, data_parallel, sampling
 
 __all__ = ["Resnet34_8s", "DenseCorrespondenceNetwork", "PixelwiseContrastiveLoss", "loss_composer",
-           "SpartanDatasetDataType", "set_default_precision", "FusedAdam", "ops", "synthetic", "data_parallel"]
+           "SpartanDatasetDataType", "set_default_precision", "FusedAdam", "ops", "synthetic", "data_parallel", "sampling"]

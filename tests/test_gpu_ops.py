@@ -297,3 +297,34 @@ def test_find_best_matches_cuda_vs_numpy_reference():
         if i < 3:
             np.testing.assert_allclose(nd[i].cpu().numpy(), ref_nd, rtol=1e-5, atol=1e-6)
     assert (int(uv[0, 0]), int(uv[0, 1])) == (20, 10) and float(diff[0]) == 0.0     # first of the two exact matches
+
+
+@pytest.mark.parametrize("mask_kind", ["blob", "none", "empty", "full", "single"])
+def test_device_non_match_sampling_matches_restated_reference(mask_kind):
+    """ddn_sample_non_matches vs the restated create_non_correspondences + create_non_matches + flatten_uv_tensor on the same
+    uniform numbers: bit-identical indices (the reference draws them with torch.rand on the CPU)."""
+    from pdc_b200 import sampling
+    H, W, Nm, k = 480, 640, 300, 150
+    gen = torch.Generator().manual_seed(31)
+    matches_a = torch.randint(0, H * W, (Nm,), generator=gen)
+    if mask_kind == "none":
+        mask = None
+    else:
+        mask = torch.zeros(H, W)
+        if mask_kind == "blob":
+            mask[100:333, 217:505] = (torch.rand(233, 288, generator=gen) > 0.3).float()
+            mask[0, 0] = 1.0; mask[H - 1, W - 1] = 2.5
+        elif mask_kind == "full":
+            mask.fill_(1.0)
+        elif mask_kind == "single":
+            mask[77, 123] = 1.0
+    ru = torch.rand(Nm * k, generator=gen); rv = torch.rand(Nm * k, generator=gen)
+    ref_a, ref_b = LO.create_non_correspondences_flat(matches_a, (H, W), k, mask, ru, rv)
+    got_a, got_b = sampling.sample_non_matches(matches_a.to(DEV), None if mask is None else mask.to(DEV), (H, W), k,
+                                               rand=(ru.to(DEV), rv.to(DEV)))
+    assert torch.equal(got_a.cpu(), ref_a) and torch.equal(got_b.cpu(), ref_b)
+    if mask is not None and mask_kind != "empty":
+        assert bool((mask.view(-1)[got_b.cpu()] != 0).all())           # every sample lies on the mask
+    # without explicit numbers: right structure and range, and the loss kernels accept the result directly
+    a2, b2 = sampling.sample_non_matches(matches_a.to(DEV), None if mask is None else mask.to(DEV), (H, W), k)
+    assert torch.equal(a2.cpu(), matches_a.repeat_interleave(k)) and int(b2.min()) >= 0 and int(b2.max()) < H * W
