@@ -80,9 +80,18 @@ EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
 def _load():
     if not os.path.exists(LIB_PATH):
-        raise ImportError(
-            "libddn_b200.so is missing at %s: build it with `python pytorch-dense-correspondence_b200/build.py` "
-            "(or __graft_entry__.build()).  There is no fallback path." % LIB_PATH)
+        # fresh checkout: compile the library in-tree (nvcc cross-compiles sm_100a without a GPU).  Still no fallback: if
+        # nvcc is not there either, importing the package fails.
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("_ddn_build", os.path.join(_HERE, "build.py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            mod.build()
+        except Exception as e:
+            raise ImportError(
+                "libddn_b200.so is missing at %s and building it failed (%s): run `python "
+                "pytorch-dense-correspondence_b200/build.py`.  There is no fallback path." % (LIB_PATH, e))
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)      # AttributeError here == header/library mismatch: fail loudly
