@@ -238,6 +238,19 @@ int ddn_sample_non_matches(const float* mask, int H, int W, const float* rand_u,
                            const int64_t* matches_a, int64_t non_matches_per_match, int64_t* out_a, int64_t* out_b,
                            void* scratch, size_t scratch_bytes, void* stream);
 
+/* Pinhole reprojection match finder for candidate pixels of image A == batch_find_pixel_correspondences
+ * (dense_correspondence/correspondence_tools/correspondence_finder.py:409-619): zero-depth, field-of-view and occlusion
+ * (3 mm margin) pruning, survivors in candidate order.  depth_* are fp32 [H*W] device arrays in raw sensor units
+ * (millimetres, DEPTH_IM_SCALE = 1000); K [9], pose_a [16], pose_b [16] are row-major HOST doubles (camera-to-world poses).
+ * out_a / out_b [n] int64 flat pixels (u + W*v; b truncated like .long()), out_u2 / out_v2 optional sub-pixel positions in B;
+ * *out_count (DEVICE int64) = number of survivors. */
+size_t ddn_find_pixel_correspondences_scratch_bytes(int64_t n);
+int ddn_find_pixel_correspondences(const float* depth_a, const float* depth_b, int H, int W,
+                                   const int64_t* candidates, int64_t n,
+                                   const double* K_host, const double* pose_a_host, const double* pose_b_host,
+                                   int64_t* out_a, int64_t* out_b, float* out_u2, float* out_v2, int64_t* out_count,
+                                   void* scratch, size_t scratch_bytes, void* stream);
+
 /* Fused Adam step over flat arrays == torch.optim.Adam(lr, betas, eps, weight_decay) as used by
  * dense_correspondence/training/training.py:133-145,346 (L2 weight decay folded into the gradient, bias-corrected moments,
  * no amsgrad).  `step` is the 1-based step count; grads are read as grads[i]*grad_scale (1/world after a SUM all-reduce). */

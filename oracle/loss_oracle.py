@@ -379,3 +379,65 @@ def create_non_correspondences_flat(matches_a_flat, image_shape, num_non_matches
     non_matches_b = v * W + u
     non_matches_a = torch.t(matches_a_flat.repeat(num_non_matches_per_match, 1)).contiguous().view(-1)
     return non_matches_a, non_matches_b
+
+
+def batch_find_pixel_correspondences(img_a_depth, img_a_pose, img_b_depth, img_b_pose, uv_a_flat, K):
+    """Restatement of correspondence_finder.batch_find_pixel_correspondences (:409-619) for given candidate pixels
+    (``uv_a_flat`` int64 flat indices), CPU float32 torch ops in the reference's order.  Depth images: float arrays in
+    millimetres.  -> (u_a, v_a) long, (u2, v2) float  (or (None, None))."""
+    import numpy
+    from numpy.linalg import inv
+    H, W = img_a_depth.shape
+
+    def invert_transform(T):        # :52-62 (numpy >= 1.13 overlap semantics: R^T and -R^T t)
+        Tc = numpy.copy(T)
+        R = numpy.transpose(Tc[0:3, 0:3]).copy()
+        Tc[0:3, 0:3] = R
+        Tc[0:3, 3] = -1.0 * R.dot(T[0:3, 3])
+        return Tc
+
+    def apply_transform_torch(vec3, T4):   # :64-68
+        ones_row = torch.ones_like(vec3[0, :]).unsqueeze(0)
+        return T4.mm(torch.cat((vec3, ones_row), 0))[0:3]
+
+    uv_a = (uv_a_flat % W, uv_a_flat // W)
+    K_inv = inv(K)
+    da = torch.from_numpy(img_a_depth.astype(numpy.float32)).view(-1, 1)
+    depth_vec = (torch.index_select(da, 0, uv_a_flat) * 1.0 / 1000.0).squeeze(1)
+    nonzero = torch.nonzero(depth_vec)
+    if nonzero.numel() == 0:
+        return None, None
+    nonzero = nonzero.squeeze(1)
+    depth_vec = torch.index_select(depth_vec, 0, nonzero)
+    u_a = torch.index_select(uv_a[0], 0, nonzero); v_a = torch.index_select(uv_a[1], 0, nonzero)
+    full_vec = torch.stack((u_a.float() * depth_vec, v_a.float() * depth_vec, depth_vec))
+    p_cam = torch.from_numpy(K_inv).float().mm(full_vec)
+    p_world = apply_transform_torch(p_cam, torch.from_numpy(numpy.asarray(img_a_pose)).float())
+    p_cam2 = apply_transform_torch(p_world, torch.from_numpy(invert_transform(numpy.asarray(img_b_pose))).float())
+    vec2 = torch.from_numpy(numpy.asarray(K)).float().mm(p_cam2)
+    u2, v2, z2 = vec2[0] / vec2[2], vec2[1] / vec2[2], vec2[2]
+    eps = 1e-3
+    u2 = torch.where(u2 < 0.0, torch.zeros_like(u2), u2); u2 = torch.where(u2 > W * 1.0 - eps, torch.zeros_like(u2), u2)
+    keep = torch.nonzero(u2)
+    if keep.numel() == 0:
+        return None, None
+    keep = keep.squeeze(1)
+    u2, v2, z2, u_a, v_a = (torch.index_select(t, 0, keep) for t in (u2, v2, z2, u_a, v_a))
+    v2 = torch.where(v2 < 0.0, torch.zeros_like(v2), v2); v2 = torch.where(v2 > H * 1.0 - eps, torch.zeros_like(v2), v2)
+    keep = torch.nonzero(v2)
+    if keep.numel() == 0:
+        return None, None
+    keep = keep.squeeze(1)
+    u2, v2, z2, u_a, v_a = (torch.index_select(t, 0, keep) for t in (u2, v2, z2, u_a, v_a))
+    db = torch.from_numpy(img_b_depth.astype(numpy.float32)).view(-1, 1)
+    uv_b_flat = v2.long() * W + u2.long()
+    depth2 = (torch.index_select(db, 0, uv_b_flat) * 1.0 / 1000).squeeze(1)
+    z2 = z2 - 0.003
+    depth2 = torch.where(depth2 < 0, torch.zeros_like(depth2), depth2)
+    depth2 = torch.where(depth2 < z2, torch.zeros_like(depth2), depth2)
+    keep = torch.nonzero(depth2)
+    if keep.numel() == 0:
+        return None, None
+    keep = keep.squeeze(1)
+    return (torch.index_select(u_a, 0, keep), torch.index_select(v_a, 0, keep)), \
+           (torch.index_select(u2, 0, keep), torch.index_select(v2, 0, keep))

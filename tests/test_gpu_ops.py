@@ -328,3 +328,43 @@ def test_device_non_match_sampling_matches_restated_reference(mask_kind):
     # without explicit numbers: right structure and range, and the loss kernels accept the result directly
     a2, b2 = sampling.sample_non_matches(matches_a.to(DEV), None if mask is None else mask.to(DEV), (H, W), k)
     assert torch.equal(a2.cpu(), matches_a.repeat_interleave(k)) and int(b2.min()) >= 0 and int(b2.max()) < H * W
+
+
+def test_device_reprojection_match_finder_vs_restated_reference():
+    """ddn_find_pixel_correspondences vs the restated batch_find_pixel_correspondences on a synthetic scene: a tilted plane
+    seen from two poses, with a depth hole, an occluder in view B and candidates partly outside B's frustum."""
+    from pdc_b200 import sampling
+    import numpy
+    H, W, n = 480, 640, 10000
+    K = numpy.array([[533.6422696034836, 0, 319.4091030774892], [0, 534.7824445233571, 236.4374299691866], [0, 0, 1.0]])
+    def pose(rx, ry, t):
+        cx, sx, cy, sy = numpy.cos(rx), numpy.sin(rx), numpy.cos(ry), numpy.sin(ry)
+        Rx = numpy.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]]); Ry = numpy.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+        T = numpy.eye(4); T[:3, :3] = Ry.dot(Rx); T[:3, 3] = t
+        return T
+    pose_a = pose(0.02, -0.03, [0.0, 0.0, 0.0]); pose_b = pose(-0.05, 0.12, [0.18, -0.04, 0.05])
+    # scene: plane z_world = 1.2 + 0.1 x - 0.05 y; render both depth images by ray casting (exact)
+    def render(T):
+        us, vs = numpy.meshgrid(numpy.arange(W), numpy.arange(H))
+        rays = numpy.linalg.inv(K).dot(numpy.stack([us.ravel(), vs.ravel(), numpy.ones(H * W)]))
+        rw = T[:3, :3].dot(rays); o = T[:3, 3]
+        nrm = numpy.array([-0.1, 0.05, 1.0]); d0 = 1.2
+        s = (d0 - nrm.dot(o)) / nrm.dot(rw)
+        return (s * 1000.0).reshape(H, W)        # depth along the optical axis = s (rays have z = 1), millimetres
+    depth_a = numpy.round(render(pose_a)).astype(numpy.float32); depth_b = numpy.round(render(pose_b)).astype(numpy.float32)
+    depth_a[200:230, 300:340] = 0.0                   # sensor hole in A
+    depth_b[100:260, 380:470] = 600.0                 # an occluder close to camera B
+    gen = torch.Generator().manual_seed(4)
+    cand = torch.randint(0, H * W, (n,), generator=gen)
+    ref_a, ref_b = LO.batch_find_pixel_correspondences(depth_a, pose_a, depth_b, pose_b, cand, K)
+    ga, gb, gu2, gv2 = sampling.find_pixel_correspondences(torch.from_numpy(depth_a).to(DEV), pose_a, torch.from_numpy(depth_b).to(DEV),
+                                                         pose_b, cand.to(DEV), K)
+    ref_a_flat = ref_a[1] * W + ref_a[0]; ref_b_flat = ref_b[1].long() * W + ref_b[0].long()
+    assert 0.3 * n < len(ref_a_flat) < 0.95 * n        # all pruning branches are exercised
+    ga, gb = ga.cpu(), gb.cpu()
+    # fp32 mat-mul rounding order (MKL vs FFMA) may flip a borderline candidate or move a match by one pixel: allow 0.2 %
+    ra = {int(a): int(b) for a, b in zip(ref_a_flat.tolist(), ref_b_flat.tolist())}
+    same = sum(1 for a, b in zip(ga.tolist(), gb.tolist()) if ra.get(a) == b)
+    assert abs(len(ga) - len(ref_a_flat)) <= 0.002 * n and same >= 0.998 * len(ref_a_flat), (len(ga), len(ref_a_flat), same)
+    if len(ga) == len(ref_a_flat) and torch.equal(ga, ref_a_flat):
+        assert float((gu2.cpu() - ref_b[0]).abs().max()) < 2e-2 and float((gv2.cpu() - ref_b[1]).abs().max()) < 2e-2
