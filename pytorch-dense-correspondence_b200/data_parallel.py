@@ -123,3 +123,58 @@ class GradientAllReducer(object):
             for g in grads:
                 g.copy_(flat[off:off + g.numel()].view_as(g))
                 off += g.numel()
+
+
+class DevicePrefetcher(object):
+    """Double-buffered host->device staging of training batches (dicts of pinned CPU tensors): the copies of batch i+1 run on
+    a side stream while batch i computes, which is what ``DataLoader(pin_memory=True)`` + ``.cuda(non_blocking=True)`` only
+    achieves when somebody issues the next copy early.  The reference copies synchronously inside the step
+    (dense_correspondence/training/training.py:311-323).  Two fixed sets of device buffers are reused (no allocation in
+    steady state; batches must keep their shapes), so a batch is valid until the next-but-one ``next()``.
+
+        for batch in DevicePrefetcher(iterable_of_dicts, device): ...     # tensors on `device`, ready on the current stream
+    """
+
+    def __init__(self, batches, device):
+        self.it = iter(batches)
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._sets = [None, None]
+        self._i = 0
+        self._next = None
+        self._preload()
+
+    def _preload(self):
+        try:
+            host = next(self.it)
+        except StopIteration:
+            self._next = None
+            return
+        slot = self._i & 1
+        self._i += 1
+        main = torch.cuda.current_stream(self.device)
+        if self._sets[slot] is None or any(torch.is_tensor(v) and (k not in self._sets[slot] or self._sets[slot][k].shape != v.shape)
+                                            for k, v in host.items()):
+            self._sets[slot] = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in host.items() if torch.is_tensor(v)}
+        # the buffers of this slot were last read by the batch handed out two calls ago: everything enqueued so far covers it
+        self.stream.wait_stream(main)
+        with torch.cuda.stream(self.stream):
+            out = {}
+            for k, v in host.items():
+                if torch.is_tensor(v):
+                    self._sets[slot][k].copy_(v, non_blocking=True)
+                    out[k] = self._sets[slot][k]
+                else:
+                    out[k] = v
+        self._next = out
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self._next is None:
+            raise StopIteration
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        batch = self._next
+        self._preload()
+        return batch

@@ -150,3 +150,41 @@ def test_oracle_bit_equal_to_reference_modules():
     assert r.layer3[0].conv1.dilation == (2, 2) and r.layer3[0].conv1.padding == (2, 2)
     assert r.layer4[0].conv1.dilation == (4, 4) and r.layer4[0].downsample[0].stride == (1, 1)
     assert r.layer2[0].conv1.stride == (2, 2) and r.layer2[0].downsample[0].stride == (2, 2)
+
+
+def test_reprojection_oracle_against_ray_cast_ground_truth():
+    """The restated batch_find_pixel_correspondences must send a pixel of A to the pixel of B that sees the same 3-D point:
+    checked against an independent float64 ray-cast of a known plane (no reference code involved)."""
+    import numpy
+    H, W, n = 240, 320, 1500
+    K = numpy.array([[266.8, 0, 159.7], [0, 267.4, 118.2], [0, 0, 1.0]])
+    def pose(rx, ry, t):
+        cx, sx, cy, sy = numpy.cos(rx), numpy.sin(rx), numpy.cos(ry), numpy.sin(ry)
+        Rx = numpy.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]]); Ry = numpy.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+        T = numpy.eye(4); T[:3, :3] = Ry.dot(Rx); T[:3, 3] = t
+        return T
+    pa, pb = pose(0.01, -0.02, [0, 0, 0]), pose(-0.04, 0.1, [0.15, -0.03, 0.04])
+    nrm, d0 = numpy.array([-0.1, 0.05, 1.0]), 1.2
+    def render(T):
+        us, vs = numpy.meshgrid(numpy.arange(W), numpy.arange(H))
+        rays = numpy.linalg.inv(K).dot(numpy.stack([us.ravel(), vs.ravel(), numpy.ones(H * W)]))
+        s = (d0 - nrm.dot(T[:3, 3])) / nrm.dot(T[:3, :3].dot(rays))
+        return (s * 1000.0).reshape(H, W)
+    da, db = render(pa).astype(numpy.float32), render(pb).astype(numpy.float32)     # unrounded depth: exact geometry
+    cand = torch.randint(0, H * W, (n,), generator=torch.Generator().manual_seed(1))
+    uv_a, uv_b = LO.batch_find_pixel_correspondences(da, pa, db, pb, cand, K)
+    assert uv_a is not None and len(uv_a[0]) > 0.5 * n
+    # ground truth in float64
+    u, v = uv_a[0].numpy().astype(numpy.float64), uv_a[1].numpy().astype(numpy.float64)
+    z = render(pa)[uv_a[1].numpy(), uv_a[0].numpy()] / 1000.0
+    pc = numpy.linalg.inv(K).dot(numpy.stack([u * z, v * z, z]))
+    pw = pa[:3, :3].dot(pc) + pa[:3, 3:4]
+    p2 = pb[:3, :3].T.dot(pw - pb[:3, 3:4])
+    q = K.dot(p2)
+    assert numpy.abs(q[0] / q[2] - uv_b[0].numpy()).max() < 2e-2 and numpy.abs(q[1] / q[2] - uv_b[1].numpy()).max() < 2e-2
+    # and the restated sampler: every sample on the mask, A side = matches repeated k times
+    mask = torch.zeros(H, W); mask[50:90, 60:200] = 1.0
+    ru, rv = torch.rand(40 * 7, generator=torch.Generator().manual_seed(2)), torch.rand(40 * 7, generator=torch.Generator().manual_seed(3))
+    ma = torch.randint(0, H * W, (40,), generator=torch.Generator().manual_seed(5))
+    na, nb = LO.create_non_correspondences_flat(ma, (H, W), 7, mask, ru, rv)
+    assert torch.equal(na, ma.repeat_interleave(7)) and bool((mask.view(-1)[nb] == 1).all())
