@@ -154,6 +154,16 @@ bn_stats_finalize_kernel(const float* __restrict__ partial, int nblk, int64_t M,
   }
 }
 
+// eval-mode BatchNorm as one multiply-add per element: y = x * scale + shift
+__global__ void bn_fold_kernel(const float* __restrict__ rm, const float* __restrict__ rv, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, int C, float eps, float* __restrict__ scale, float* __restrict__ shift) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float sc = gamma[c] * (1.0f / sqrtf(rv[c] + eps));
+  scale[c] = sc;
+  shift[c] = fmaf(-rm[c], sc, beta[c]);
+}
+
 __global__ void bn_eval_stats_kernel(const float* __restrict__ rm, const float* __restrict__ rv, int C, float eps,
                                      float* __restrict__ mean, float* __restrict__ invstd) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -357,6 +367,12 @@ int launch_bn_stats_finalize(const float* partial, int nblk, int64_t M, int C, f
 
 int launch_bn_eval_stats(const float* rm, const float* rv, int C, float eps, float* mean, float* invstd, cudaStream_t st) {
   DDN_LAUNCH(bn_eval_stats_kernel, (int)ceil_div(C, 128), 128, 0, st, rm, rv, C, eps, mean, invstd);
+  return 0;
+}
+
+int launch_bn_fold(const float* rm, const float* rv, const float* gamma, const float* beta, int C, float eps,
+                   float* scale, float* shift, cudaStream_t st) {
+  DDN_LAUNCH(bn_fold_kernel, (int)ceil_div(C, 128), 128, 0, st, rm, rv, gamma, beta, C, eps, scale, shift);
   return 0;
 }
 

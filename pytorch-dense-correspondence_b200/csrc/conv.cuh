@@ -31,6 +31,9 @@ int launch_bn_stats_finalize(const float* partial, int nblk, int64_t M, int C, f
                              float* running_mean, float* running_var, float momentum, float eps, cudaStream_t st);
 int launch_bn_eval_stats(const float* running_mean, const float* running_var, int C, float eps,
                          float* mean, float* invstd, cudaStream_t st);
+// eval-mode BN folded to y = x*scale + shift (scale = gamma/sqrt(rv+eps), shift = beta - rm*scale)
+int launch_bn_fold(const float* running_mean, const float* running_var, const float* gamma, const float* beta, int C, float eps,
+                   float* scale, float* shift, cudaStream_t st);
 // y = relu?( (x-mean)*invstd*gamma+beta + res ), res = r (identity) or (r-rmean)*rinvstd*rgamma+rbeta
 struct BnApplyArgs {
   const float* x; const float* mean; const float* invstd; const float* gamma; const float* beta;

@@ -132,6 +132,10 @@ struct TcConvParams {
   int stride;            // 1, or 2 (forward only: the A tensor map then samples every other input pixel)
   int tiles_h, tiles_w;
   float* bn_partial;     // optional [2][gridDim.x][Cout]: per-tile column sums / sums of squares of the conv output
+  // optional folded epilogue (inference, BatchNorm in eval mode): y = relu?(acc * ep_scale[c] + ep_shift[c] + addend),
+  // written as fp32 (`out`, may be null then) and / or as bf16 hi/lo operand planes for the next conv
+  const float* ep_scale; const float* ep_shift; int ep_relu;
+  __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
 };
 
 // After the call, a[0] on lane l holds the sum over the 32 lanes of column l (butterfly reduce-scatter, 31 shuffles).
@@ -308,6 +312,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 // epilogue warps drain accumulator i (TMEM -> registers -> global, BN column sums) the MMA warp is already filling
 // accumulator i+1 and the TMA warp runs ahead through the shared-memory ring.  TMEM allocation, barrier setup and
 // descriptor prefetch are paid once per SM instead of once per tile.
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -442,18 +449,45 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __g
       tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N / 32; ++c) {
+        // the addend (residual-branch gradient) of this chunk first: its global-load latency overlaps the TMEM read
+        float4 adv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          adv[j] = (ad && ok) ? __ldg(reinterpret_cast<const float4*>(ad + c * 32) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BLOCK_N + c * 32), v);
-        if (ok) {
+        if (p.ep_scale) {        // folded BatchNorm (+ residual, ReLU): the conv output never exists un-normalised
+          const float4* sc = reinterpret_cast<const float4*>(p.ep_scale + co0 + c * 32);
+          const float4* sh = reinterpret_cast<const float4*>(p.ep_shift + co0 + c * 32);
+          uint32_t hp[16], lp[16];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 f = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-            if (ad) {
-              float4 a = __ldg(reinterpret_cast<const float4*>(ad + c * 32 + j));
-              f.x += a.x; f.y += a.y; f.z += a.z; f.w += a.w;
-            }
-            *reinterpret_cast<float4*>(o + c * 32 + j) = f;
+          for (int j = 0; j < 8; ++j) {
+            const float4 a = __ldg(sc + j), b = __ldg(sh + j);
+            float4 f = make_float4(fmaf(__uint_as_float(v[4 * j]), a.x, b.x) + adv[j].x, fmaf(__uint_as_float(v[4 * j + 1]), a.y, b.y) + adv[j].y,
+                                   fmaf(__uint_as_float(v[4 * j + 2]), a.z, b.z) + adv[j].z, fmaf(__uint_as_float(v[4 * j + 3]), a.w, b.w) + adv[j].w);
+            if (p.ep_relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f); }
+            if (ok && p.out) reinterpret_cast<float4*>(o + c * 32)[j] = f;
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(f.x), h1 = __float2bfloat16_rn(f.y), h2 = __float2bfloat16_rn(f.z), h3 = __float2bfloat16_rn(f.w);
+            hp[2 * j] = pack_bf16x2(h0, h1); hp[2 * j + 1] = pack_bf16x2(h2, h3);
+            lp[2 * j] = pack_bf16x2(__float2bfloat16_rn(f.x - __bfloat162float(h0)), __float2bfloat16_rn(f.y - __bfloat162float(h1)));
+            lp[2 * j + 1] = pack_bf16x2(__float2bfloat16_rn(f.z - __bfloat162float(h2)), __float2bfloat16_rn(f.w - __bfloat162float(h3)));
           }
+          if (ok && p.out_hi) {
+            uint4* oh = reinterpret_cast<uint4*>(p.out_hi + pix * p.Cout + co0 + c * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) oh[j] = make_uint4(hp[4 * j], hp[4 * j + 1], hp[4 * j + 2], hp[4 * j + 3]);
+            if (p.out_lo) {
+              uint4* ol = reinterpret_cast<uint4*>(p.out_lo + pix * p.Cout + co0 + c * 32);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) ol[j] = make_uint4(lp[4 * j], lp[4 * j + 1], lp[4 * j + 2], lp[4 * j + 3]);
+            }
+          }
+        } else if (ok) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            reinterpret_cast<float4*>(o + c * 32)[j] =
+                make_float4(__uint_as_float(v[4 * j]) + adv[j].x, __uint_as_float(v[4 * j + 1]) + adv[j].y,
+                            __uint_as_float(v[4 * j + 2]) + adv[j].z, __uint_as_float(v[4 * j + 3]) + adv[j].w);
         }
         if (p.bn_partial) {
           float a[32], b[32];
@@ -930,6 +964,16 @@ int tc_wgrad_planes(TcPlanes x, TcPlanes dy, float* dw, int N, int H, int W, int
 }
 
 bool tc_available() { return true; }
+static bool tc_persistent_enabled() {
+  static int persistent = -1;
+  if (persistent < 0) { const char* e = getenv("DDN_TC_PERSISTENT"); persistent = (e && e[0] == '0') ? 0 : 1; }
+  return persistent != 0;
+}
+bool tc_folded_epilogue_supported() {      // DDN_FOLD_BN=0: keep the separate eval-mode BN pass (A/B measurements)
+  static int fold = -1;
+  if (fold < 0) { const char* e = getenv("DDN_FOLD_BN"); fold = (e && e[0] == '0') ? 0 : 1; }
+  return fold != 0 && tc_persistent_enabled();
+}
 
 // forward / weight-gradient coverage: 3x3 (pad == dil) or 1x1 (pad 0), stride 1 -- or stride 2 with dil 1 on even sizes
 bool tc_conv_supported(int Cin, int Cout, int k, int stride, int pad, int dil, int H, int W) {
@@ -989,9 +1033,7 @@ static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUt
     DDN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  static int persistent = -1;
-  if (persistent < 0) { const char* e = getenv("DDN_TC_PERSISTENT"); persistent = (e && e[0] == '0') ? 0 : 1; }
-  if (persistent) {
+  if (tc_persistent_enabled()) {
     constexpr int PSTAGES = (192 * 1024) / STAGE_BYTES >= 8 ? 8 : (192 * 1024) / STAGE_BYTES;
     const size_t psmem = (size_t)PSTAGES * STAGE_BYTES + 1024;
     static bool pconfigured = false;
@@ -1017,7 +1059,7 @@ static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUt
 //   bn_partial (forward only): [2][tc_bn_partial_blocks(N,Ho,Wo)][Cout] column sums.
 int tc_conv_planes(TcPlanes in, const float* w_oihw, const TcPlanes* wpk, float* out, const float* addend, float* bn_partial,
                    int N, int H, int W, int Cin, int Cout, int k, int stride, int dil, int dgrad, int precision,
-                   void* wws, size_t wws_bytes, cudaStream_t st) {
+                   void* wws, size_t wws_bytes, cudaStream_t st, const TcFoldedEpilogue* ep) {
   DDN_CHECK_ARG(stride == 1 || !dgrad, "the strided data gradient goes through zero-inserted planes (stride 1 here)");
   const int Ho = H / stride, Wo = W / stride;
   const double fl = 2.0 * N * Ho * Wo * (double)Cout * k * k * Cin;
@@ -1048,6 +1090,14 @@ int tc_conv_planes(TcPlanes in, const float* w_oihw, const TcPlanes* wpk, float*
   p.stride = stride;
   p.tiles_h = (int)ceil_div(Ho, TC_TH); p.tiles_w = (int)ceil_div(Wo, TC_TW);
   p.bn_partial = bn_partial;
+  p.ep_scale = nullptr; p.ep_shift = nullptr; p.ep_relu = 0; p.out_hi = nullptr; p.out_lo = nullptr;
+  if (ep) {
+    DDN_CHECK_ARG(!dgrad && !bn_partial && ep->scale && ep->shift && (out || ep->out_hi), "folded epilogue: forward only, needs scale/shift and an output");
+    DDN_CHECK_ARG(tc_folded_epilogue_supported(), "the folded epilogue needs the persistent kernel (DDN_TC_PERSISTENT=0 is set)");
+    p.ep_scale = ep->scale; p.ep_shift = ep->shift; p.ep_relu = ep->relu; p.out_hi = ep->out_hi; p.out_lo = want_lo ? ep->out_lo : nullptr;
+  } else {
+    DDN_CHECK_ARG(out != nullptr, "conv output pointer is null");
+  }
   ProfScope ps(dgrad ? PROF_CONV_DGRAD_TC : PROF_CONV_FWD_TC, fl, st);   // times the MMA kernel only
   if (want_lo) {
     if (block_n == 128) return launch_tc<128, 3>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);

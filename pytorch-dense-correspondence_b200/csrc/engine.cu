@@ -311,6 +311,20 @@ static int conv_bn_forward(const Ctx& c, const ConvSpec& cs, const BnSpec& bs, c
   return launch_bn_eval_stats(rm, rv, bs.C, c.eps, c.f(cb.mean), c.f(cb.invstd), c.st);
 }
 
+// Inference (eval-mode BN) on the tensor-core path: BN is a per-channel multiply-add of the conv accumulator, so the conv
+// epilogue applies it together with the residual add and the ReLU and writes the next conv's operand planes itself; no
+// un-normalised conv output and no separate BN pass exist.  `out` / `out_p` may be absent (null / {0,0}).
+static int conv_bn_folded(const Ctx& c, const ConvSpec& cs, const BnSpec& bs, const PlaneBufs& in_p, const ConvBufs& cb, int N,
+                          float* out, const PlaneBufs* out_p, const float* addend, int relu) {
+  float* scale = c.f(cb.mean); float* shift = c.f(cb.invstd);     // the per-conv statistics slots hold scale / shift here
+  DDN_TRY(launch_bn_fold(c.buffers + bs.rm_off, c.buffers + bs.rv_off, c.params + bs.g_off, c.params + bs.b_off, bs.C, c.eps,
+                         scale, shift, c.st));
+  TcPlanes wpk_s; const TcPlanes* wpk = cached_pack(c, cs, 0, &wpk_s);
+  TcFoldedEpilogue ep = {scale, shift, relu, out_p ? c.h(out_p->hi) : nullptr, out_p ? c.h(out_p->lo) : nullptr};
+  return tc_conv_planes(c.planes(in_p), c.params + cs.w_off, wpk, out, addend, nullptr, N, cb.Hin, cb.Win, cs.cin, cs.cout, cs.k,
+                        cs.stride, cs.dil, 0, c.p->precision, c.ws + c.p->wws, tc_weight_ws_bytes(), c.st, &ep);
+}
+
 static int net_forward(const Ctx& c, const float* x, float* y) {
   const NetSpec& s = *c.s; const Plan& p = *c.p;
   const int B = p.B;
@@ -338,9 +352,23 @@ static int net_forward(const Ctx& c, const float* x, float* y) {
   const float* cur = c.f(p.pool_out);
   PlaneBufs cur_p = p.pool_p;
   const bool want_lo = p.precision == DDN_PRECISION_BF16X3;
+  const bool fold = !c.training && p.tc && tc_folded_epilogue_supported();
   for (size_t i = 0; i < s.blocks.size(); ++i) {        // BasicBlock.forward, resnet.py:53-69
     const BlockSpec& b = s.blocks[i]; const BlockBufs& bb = p.blk[i];
     int64_t M1 = (int64_t)B * bb.c1.Hout * bb.c1.Wout;
+    if (fold && conv_on_tc(c, b.c1, bb.c1.Hin, bb.c1.Win) && conv_on_tc(c, b.c2, bb.c2.Hin, bb.c2.Win) &&
+        (!b.has_ds || conv_on_tc(c, b.ds, bb.ds.Hin, bb.ds.Win))) {
+      DDN_TRY(conv_bn_folded(c, b.c1, b.b1, cur_p, bb.c1, B, nullptr, &bb.act1_p, nullptr, 1));       // act1: planes only
+      const float* res = cur;
+      if (b.has_ds) {
+        DDN_TRY(conv_bn_folded(c, b.ds, b.bd, cur_p, bb.ds, B, c.f(bb.ds.raw), nullptr, nullptr, 0));  // bn_d(conv_d(x)), fp32
+        res = c.f(bb.ds.raw);
+      }
+      DDN_TRY(conv_bn_folded(c, b.c2, b.b2, bb.act1_p, bb.c2, B, c.f(bb.out), &bb.out_p, res, 1));
+      cur = c.f(bb.out);
+      cur_p = bb.out_p;
+      continue;
+    }
     DDN_TRY(conv_bn_forward(c, b.c1, b.b1, cur, cur_p, bb.c1, B, b.c1.cin));
     BnApplyArgs a1 = {c.f(bb.c1.raw), c.f(bb.c1.mean), c.f(bb.c1.invstd), c.params + b.b1.g_off, c.params + b.b1.b_off,
                       nullptr, nullptr, nullptr, nullptr, nullptr, c.f(bb.act1), M1, b.b1.C, 1,
