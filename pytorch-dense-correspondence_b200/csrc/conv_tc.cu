@@ -81,6 +81,19 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// K-major descriptor for a k-block of BK bf16 per row: BK = 64 -> 128-byte rows, SWIZZLE_128B (layout 2, SBO 1024);
+// BK = 32 -> 64-byte rows, SWIZZLE_64B (layout 4, SBO 512).  Canonical layouts: cute/atom/mma_traits_sm100.hpp, Major-K.
+template <int BK>
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
+  static_assert(BK == 64 || BK == 32, "k-block must be one 128-byte or one 64-byte swizzle row");
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((8 * BK * 2) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(BK == 64 ? 2 : 4) << 61;
+  return d;
+}
 // Instruction descriptor for kind::f16 (cute::UMMA::InstrDescriptor): fp32 accumulate, bf16 x bf16, both K-major.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -319,14 +332,15 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-template <int BLOCK_N, int NPROD>
+template <int BLOCK_N, int NPROD, int BK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                           const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                           const TcConvParams p) {
   constexpr int NSPLIT = NPROD == 3 ? 2 : 1;
-  constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
-  constexpr int STAGE_BYTES = NSPLIT * (TC_A_BYTES + B_BYTES);
+  constexpr int A_BYTES = 128 * BK * 2;
+  constexpr int B_BYTES = BLOCK_N * BK * 2;
+  constexpr int STAGE_BYTES = NSPLIT * (A_BYTES + B_BYTES);
   constexpr int STAGES = (192 * 1024) / STAGE_BYTES >= 8 ? 8 : (192 * 1024) / STAGE_BYTES;
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
   constexpr uint32_t IDESC = make_idesc_bf16(128, BLOCK_N);
@@ -345,7 +359,7 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __g
   const int n_co = p.Cout / BLOCK_N;
   const int n_sp = p.N * p.tiles_h * p.tiles_w;
   const int total_tiles = n_sp * n_co;
-  const int cin_chunks = p.Cin / TC_BLOCK_K;
+  const int cin_chunks = p.Cin / BK;
   const int num_kb = p.taps_w * p.taps_w * cin_chunks;
   const int half = p.taps_w >> 1;
 
@@ -384,11 +398,11 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __g
           uint8_t* st = smem + (size_t)s * STAGE_BYTES;
           const uint32_t bar = smem_u32(&full_bar[s]);
           mbar_expect_tx(bar, STAGE_BYTES);
-          tma_load_4d(smem_u32(st), &tm_a_hi, bar, cc * TC_BLOCK_K, ww, hh, n);
-          tma_load_2d(smem_u32(st + NSPLIT * TC_A_BYTES), &tm_b_hi, bar, kb * TC_BLOCK_K, co0);
+          tma_load_4d(smem_u32(st), &tm_a_hi, bar, cc * BK, ww, hh, n);
+          tma_load_2d(smem_u32(st + NSPLIT * A_BYTES), &tm_b_hi, bar, kb * BK, co0);
           if (NSPLIT == 2) {
-            tma_load_4d(smem_u32(st + TC_A_BYTES), &tm_a_lo, bar, cc * TC_BLOCK_K, ww, hh, n);
-            tma_load_2d(smem_u32(st + 2 * TC_A_BYTES + B_BYTES), &tm_b_lo, bar, kb * TC_BLOCK_K, co0);
+            tma_load_4d(smem_u32(st + A_BYTES), &tm_a_lo, bar, cc * BK, ww, hh, n);
+            tma_load_2d(smem_u32(st + 2 * A_BYTES + B_BYTES), &tm_b_lo, bar, kb * BK, co0);
           }
         }
       }
@@ -408,12 +422,12 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __g
           mbar_wait(smem_u32(&full_bar[s]), (g / STAGES) & 1);
           tc_fence_after();
           const uint32_t st = smem_u32(smem + (size_t)s * STAGE_BYTES);
-          const uint64_t a_hi = make_kmajor_sw128_desc(st);
-          const uint64_t b_hi = make_kmajor_sw128_desc(st + NSPLIT * TC_A_BYTES);
-          const uint64_t a_lo = make_kmajor_sw128_desc(st + TC_A_BYTES);
-          const uint64_t b_lo = make_kmajor_sw128_desc(st + 2 * TC_A_BYTES + B_BYTES);
+          const uint64_t a_hi = make_kmajor_desc<BK>(st);
+          const uint64_t b_hi = make_kmajor_desc<BK>(st + NSPLIT * A_BYTES);
+          const uint64_t a_lo = make_kmajor_desc<BK>(st + A_BYTES);
+          const uint64_t b_lo = make_kmajor_desc<BK>(st + 2 * A_BYTES + B_BYTES);
 #pragma unroll
-          for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
+          for (int k = 0; k < BK / 16; ++k) {
             const uint64_t adv = (uint64_t)((k * 32) >> 4);
             if (NPROD == 3) {
               umma_bf16(acc, a_hi + adv, b_lo + adv, IDESC, (kb | k) != 0);
@@ -505,8 +519,7 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __g
       if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
       if (p.bn_partial) {
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int e = threadIdx.x - 64;
-        if (e < BLOCK_N) {
+        for (int e = threadIdx.x - 64; e < BLOCK_N; e += 128) {
           const float s0 = s_part[buf][0][0][e] + s_part[buf][0][1][e] + s_part[buf][0][2][e] + s_part[buf][0][3][e];
           const float s1 = s_part[buf][1][0][e] + s_part[buf][1][1][e] + s_part[buf][1][2][e] + s_part[buf][1][3][e];
           p.bn_partial[(size_t)sp * p.Cout + co0 + e] = s0;
@@ -874,28 +887,31 @@ static EncodeTiledFn get_encode_fn() {
 
 // `sample` = traversal stride in W and H (elementStrides): a box then spans box*sample input pixels and delivers every
 // sample-th one, which is how a stride-2 convolution reads its input without a strided copy.
-static int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int box_h = TC_TH, int sample = 1) {
+static int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int box_h = TC_TH, int sample = 1,
+                        int bk = TC_BLOCK_K) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)"); return DDN_EUNSUPPORTED; }
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {TC_BLOCK_K, (cuuint32_t)(TC_TW * sample), (cuuint32_t)(box_h * sample), 1};
+  cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(TC_TW * sample), (cuuint32_t)(box_h * sample), 1};
   cuuint32_t es[4] = {1, (cuuint32_t)sample, (cuuint32_t)sample, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activations) failed: %d", (int)r); return DDN_EINVAL; }
   return 0;
 }
-static int make_weight_map(CUtensorMap* m, const void* base, int rows, int K, int block_n) {
+static int make_weight_map(CUtensorMap* m, const void* base, int rows, int K, int block_n, int bk = TC_BLOCK_K) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)"); return DDN_EUNSUPPORTED; }
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-  cuuint32_t box[2] = {TC_BLOCK_K, (cuuint32_t)block_n};
+  cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)block_n};
   cuuint32_t es[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return DDN_EINVAL; }
   return 0;
@@ -1021,9 +1037,28 @@ int tc_stem_patches(const float* x_nchw, __nv_bfloat16* hi, __nv_bfloat16* lo, i
   return 0;
 }
 
+template <int BLOCK_N, int NPROD, int BK>
+static int launch_tc_persistent(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                                const TcConvParams& p, cudaStream_t st) {
+  constexpr int NSPLIT = NPROD == 3 ? 2 : 1;
+  constexpr int STAGE_BYTES = NSPLIT * (128 * BK * 2 + BLOCK_N * BK * 2);
+  constexpr int PSTAGES = (192 * 1024) / STAGE_BYTES >= 8 ? 8 : (192 * 1024) / STAGE_BYTES;
+  const size_t psmem = (size_t)PSTAGES * STAGE_BYTES + 1024;
+  static bool pconfigured = false;
+  if (!pconfigured) {
+    DDN_CUDA(cudaFuncSetAttribute(conv_tc_persistent_kernel<BLOCK_N, NPROD, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+    pconfigured = true;
+  }
+  const int total = p.N * p.tiles_h * p.tiles_w * (p.Cout / BLOCK_N);
+  const int grid = std::min(total, num_sms());
+  DDN_LAUNCH((conv_tc_persistent_kernel<BLOCK_N, NPROD, BK>), grid, TC_THREADS, psmem, st, a_hi, a_lo, b_hi, b_lo, p);
+  return 0;
+}
+
 template <int BLOCK_N, int NPROD>
 static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
                      const TcConvParams& p, cudaStream_t st) {
+  if (tc_persistent_enabled()) return launch_tc_persistent<BLOCK_N, NPROD, TC_BLOCK_K>(a_hi, a_lo, b_hi, b_lo, p, st);
   constexpr int NSPLIT = NPROD == 3 ? 2 : 1;
   constexpr int STAGE_BYTES = NSPLIT * (TC_A_BYTES + BLOCK_N * TC_BLOCK_K * 2);
   constexpr int STAGES = (200 * 1024) / STAGE_BYTES >= 8 ? 8 : (200 * 1024) / STAGE_BYTES;
@@ -1033,22 +1068,19 @@ static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUt
     DDN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  if (tc_persistent_enabled()) {
-    constexpr int PSTAGES = (192 * 1024) / STAGE_BYTES >= 8 ? 8 : (192 * 1024) / STAGE_BYTES;
-    const size_t psmem = (size_t)PSTAGES * STAGE_BYTES + 1024;
-    static bool pconfigured = false;
-    if (!pconfigured) {
-      DDN_CUDA(cudaFuncSetAttribute(conv_tc_persistent_kernel<BLOCK_N, NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-      pconfigured = true;
-    }
-    const int total = p.N * p.tiles_h * p.tiles_w * (p.Cout / BLOCK_N);
-    const int grid = std::min(total, num_sms());
-    DDN_LAUNCH((conv_tc_persistent_kernel<BLOCK_N, NPROD>), grid, TC_THREADS, psmem, st, a_hi, a_lo, b_hi, b_lo, p);
-    return 0;
-  }
   dim3 grid((unsigned)(p.N * p.tiles_h * p.tiles_w), (unsigned)(p.Cout / BLOCK_N));
   DDN_LAUNCH((conv_tc_kernel<BLOCK_N, NPROD>), grid, TC_THREADS, smem, st, a_hi, a_lo, b_hi, b_lo, p);
   return 0;
+}
+
+// 256-wide tiles (persistent kernel only; opt-in with DDN_TC_N256=1): one A tile feeds twice the output channels and k-blocks
+// of 32 (64-byte swizzle rows) keep 4 pipeline stages.  Measured neutral on B200 (profiles/r1_tile_n256_ab.json: the
+// 128-wide kernel is not limited by shared-memory operand reads, and 256-wide tiles quantise worse over 148 SMs), so the
+// default stays 128; kept because it is the single-CTA half of a future cta_group::2 256x256 tile.
+static bool tc_wide_tiles_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DDN_TC_N256"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v != 0 && tc_persistent_enabled();
 }
 
 // out[N,Ho,Wo,gout] = conv(planes of in[N,H,W,gin]) (+ addend).
@@ -1079,12 +1111,13 @@ int tc_conv_planes(TcPlanes in, const float* w_oihw, const TcPlanes* wpk, float*
     DDN_LAUNCH(pack_weights_tc_kernel, wblocks, 256, 0, st, w_oihw, ph, pl, Cout, Cin, k, dgrad, want_lo);
     b_hi = ph; b_lo = pl;
   }
-  const int block_n = gout % 128 == 0 ? 128 : 64;
+  const int block_n = (gout % 256 == 0 && tc_wide_tiles_enabled()) ? 256 : gout % 128 == 0 ? 128 : 64;
+  const int bk = block_n == 256 ? 32 : TC_BLOCK_K;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  DDN_TRY(make_act_map(&ma_hi, in.hi, N, H, W, gin, TC_TH, stride));
-  DDN_TRY(make_act_map(&ma_lo, want_lo ? in.lo : in.hi, N, H, W, gin, TC_TH, stride));
-  DDN_TRY(make_weight_map(&mb_hi, b_hi, gout, k * k * gin, block_n));
-  DDN_TRY(make_weight_map(&mb_lo, want_lo ? b_lo : b_hi, gout, k * k * gin, block_n));
+  DDN_TRY(make_act_map(&ma_hi, in.hi, N, H, W, gin, TC_TH, stride, bk));
+  DDN_TRY(make_act_map(&ma_lo, want_lo ? in.lo : in.hi, N, H, W, gin, TC_TH, stride, bk));
+  DDN_TRY(make_weight_map(&mb_hi, b_hi, gout, k * k * gin, block_n, bk));
+  DDN_TRY(make_weight_map(&mb_lo, want_lo ? b_lo : b_hi, gout, k * k * gin, block_n, bk));
   TcConvParams p;
   p.out = out; p.addend = addend; p.N = N; p.H = Ho; p.W = Wo; p.Cin = gin; p.Cout = gout; p.taps_w = k; p.dil = dil;
   p.stride = stride;
@@ -1100,9 +1133,11 @@ int tc_conv_planes(TcPlanes in, const float* w_oihw, const TcPlanes* wpk, float*
   }
   ProfScope ps(dgrad ? PROF_CONV_DGRAD_TC : PROF_CONV_FWD_TC, fl, st);   // times the MMA kernel only
   if (want_lo) {
+    if (block_n == 256) return launch_tc_persistent<256, 3, 32>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);
     if (block_n == 128) return launch_tc<128, 3>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);
     return launch_tc<64, 3>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);
   }
+  if (block_n == 256) return launch_tc_persistent<256, 1, 32>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);
   if (block_n == 128) return launch_tc<128, 1>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);
   return launch_tc<64, 1>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);
 }
