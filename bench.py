@@ -220,7 +220,10 @@ def run_ours(args):
     dcn = pdc_b200.DenseCorrespondenceNetwork.from_config(cfg, load_stored_params=False)
     dcn.fcn.precision = prec
     DP.broadcast_parameters(dcn)
-    pcl = pdc_b200.PixelwiseContrastiveLoss(image_shape=dcn.image_shape, config=dict(LO.DEFAULT_LOSS_CONFIG))
+    loss_cfg = dict(LO.DEFAULT_LOSS_CONFIG)
+    if args.l2_pixel_loss:
+        loss_cfg["use_l2_pixel_loss_on_masked_non_matches"] = True
+    pcl = pdc_b200.PixelwiseContrastiveLoss(image_shape=dcn.image_shape, config=loss_cfg)
     reducer = DP.GradientAllReducer(dcn.parameters())
     host = synthetic.make_pair_batch(Bp, H, W, args.matches, args.non_matches, args.non_matches, 0, seed=1 + rank)
     keys = [k for k, v in host.items() if v is not None]
@@ -332,16 +335,18 @@ def run_ours(args):
         cpu = {"value": rate, "unit": "pairs/s", "cores": cores, "kind": "port",
                "sample": "oracle port, single pairs of the same workload: 3 timed fwd+loss+bwd steps (median) after 1 warm-up; "
                          "fwd+loss only = %.3f pairs/s; %.1f s of CPU wall" % (rate_fwd, time.perf_counter() - t0)}
+    workload_name = ("configs[1]" if (D == 3 and Bp == 8 and args.non_matches == 1000 and not args.l2_pixel_loss) else
+                     "configs[4] per-GPU shard" if (D == 8 and Bp == 4 and args.non_matches == 5000) else "custom")
     line = {
         "metric": "image-pairs/s (640x480, D=%d) fwd+loss+bwd" % D, "value": value, "unit": "pairs/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"fp32": "f32", "bf16x3": "f32 (bf16x3 split on tcgen05, fp32 accumulate)", "bf16": "bf16"}[prec_name],
         "data": "synthetic",
-        "config": {"workload": "configs[1]: batch %d pairs/GPU, Resnet34_8s D=%d, %dx%d, train-mode BN, %d matches + %d masked + "
+        "config": {"workload": workload_name + ": batch %d pairs/GPU, Resnet34_8s D=%d, %dx%d, train-mode BN, %d matches + %d masked + "
                                "%d background non-matches per pair, loss_composer.get_loss within-scene, no optimizer step" %
                                (Bp, D, W, H, args.matches, args.non_matches, args.non_matches),
-                   "global_batch_pairs": world * Bp, "parallelism": "dp%d" % world, "precision": prec_name,
+                   "l2_pixel_loss_on_masked_non_matches": bool(args.l2_pixel_loss), "global_batch_pairs": world * Bp, "parallelism": "dp%d" % world, "precision": prec_name,
                    "l2": "inputs+activations touched per step (~%.1f GB) are far larger than the 126 MB L2; no explicit flush" %
                          (N.lib.ddn_resnet34_8s_workspace_bytes(Bp, H, W, D, 1, prec) * 2 / 1e9)},
         "clocks": clk.summary(),
@@ -371,6 +376,8 @@ def main():
     ap.add_argument("--non-matches", type=int, default=1000)
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--l2-pixel-loss", action="store_true",
+                    help="configs[4] variant: use_l2_pixel_loss_on_masked_non_matches=True (M_pixel=50)")
     ap.add_argument("--profile-run", action="store_true",
                     help="short run for ncu: 1 warm-up + --steps timed steps, no e2e / cpu legs (numbers printed are NOT bench values)")
     args = ap.parse_args()

@@ -18,7 +18,7 @@ peaks = json.load(open(pk)) if os.path.exists(pk) else {}
 peak_tf = float(peaks.get("bf16_tflops_sustained", 1441.5))
 B, D, H, W = int(os.environ.get("FWD_BATCH", "16")), 3, 480, 640
 GF_IMG = 211.909
-steps, warmup = 20, 5
+steps, warmup = int(os.environ.get("FWD_STEPS", "20")), int(os.environ.get("FWD_WARMUP", "5"))
 
 torch.manual_seed(0)
 net = pdc_b200.Resnet34_8s(num_classes=D).cuda()
