@@ -1,6 +1,6 @@
 """Per-parameter gradient error: ours (GPU) vs CPU oracle, next to torch-GPU oracle vs CPU oracle (noise floor)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import pdc_b200
 from pdc_b200 import _native as N
