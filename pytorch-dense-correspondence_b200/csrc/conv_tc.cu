@@ -535,6 +535,275 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __g
   }
 }
 
+// ------------------------------------------------------------------------------------------------ CTA-pair conv
+// EXPERIMENTAL (DDN_TC_2CTA=1; off by default; compiled and reviewed but NOT yet run on hardware -- round 1's GPU budget was
+// spent when it was written; its parity run is the first task of round 2).  Same contraction as conv_tc_persistent_kernel
+// with `tcgen05.mma.cta_group::2`: a cluster of two CTAs (two SMs of one TPC) owns a 256-pixel x BLOCK_N-channel tile -- the
+// same 8x16 spatial tile of two consecutive images.  CTA r stages its own image's A tile (128 pixels x 64 ch) and HALF of the
+// B tile (BLOCK_N/2 weight rows); the leader's MMA reads A from both CTAs' shared memory as the two M halves and the two B
+// halves as one N = BLOCK_N operand, and each CTA's TMEM receives its own 128 pixels x BLOCK_N channels.  Per SM and k-block
+// that is 32 KB (A hi/lo) + BLOCK_N/2 x 256 B of operands for 128 x BLOCK_N x 64 MACs: 5.1 KB/MFLOP at BLOCK_N = 256 against
+// 10.2 for the single-CTA 128x128 tile, which is bound by exactly that ingest.
+// Barrier protocol (cutlass sm100 2-SM GEMMs): both producers' TMA loads complete_tx on the LEADER's full barrier (address
+// with the peer bit cleared), the leader arms it with expect_tx for both CTAs' bytes and the peer arrives on it remotely;
+// the leader's tcgen05.commit multicasts to the empty / accumulator-full barriers of both CTAs; the epilogue warps of both
+// CTAs arrive on the leader's accumulator-empty barrier.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;     // cute::Sm100MmaPeerBitMask: shared::cluster address of the even (leader) CTA
+
+__device__ __forceinline__ uint32_t cluster_cta_rank() {
+  uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta_rank) {   // arrive on the barrier at `bar` in CTA cta_rank
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 remote;\n\t"
+      "mapa.shared::cluster.u32 remote, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [remote];\n\t"
+      "}\n" ::"r"(bar), "r"(cta_rank) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {     // arrives on `bar` (same offset) in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+template <int BLOCK_N, int NPROD>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                    const TcConvParams p) {
+  constexpr int NSPLIT = NPROD == 3 ? 2 : 1;
+  constexpr int HALF_N = BLOCK_N / 2;                       // weight rows staged by each CTA
+  constexpr int A_BYTES = 128 * TC_BLOCK_K * 2;
+  constexpr int B_BYTES = HALF_N * TC_BLOCK_K * 2;
+  constexpr int STAGE_BYTES = NSPLIT * (A_BYTES + B_BYTES);  // per CTA
+  constexpr int STAGES = (192 * 1024) / STAGE_BYTES >= 8 ? 8 : (192 * 1024) / STAGE_BYTES;
+  static_assert(STAGES >= 2, "pipeline needs at least two stages");
+  static_assert(2 * BLOCK_N <= 512, "two accumulators must fit the 512 TMEM columns");
+  constexpr uint32_t IDESC = make_idesc_bf16(256, BLOCK_N);  // M = 256 across the pair
+  constexpr int NCOLS = 2 * BLOCK_N;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t full_bar[STAGES];     // used in the leader only
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t acc_full[2];
+  __shared__ __align__(8) uint64_t acc_empty[2];         // used in the leader only
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_part[2][2][4][BLOCK_N];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_cta_rank();
+  const bool leader = rank == 0;
+  const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int n_co = p.Cout / BLOCK_N;
+  const int n_img_pairs = (p.N + 1) >> 1;
+  const int n_sp = p.N * p.tiles_h * p.tiles_w;            // rows of the BN partial buffer (one per image tile, as in the 1-CTA kernel)
+  const int total_tiles = n_img_pairs * p.tiles_h * p.tiles_w * n_co;
+  const int cin_chunks = p.Cin / TC_BLOCK_K;
+  const int num_kb = p.taps_w * p.taps_w * cin_chunks;
+  const int half = p.taps_w >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), 2); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&acc_full[b]), 1); mbar_init(smem_u32(&acc_empty[b]), 8); }
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_b_hi);
+    if (NSPLIT == 2) { tma_prefetch_desc(&tm_a_lo); tma_prefetch_desc(&tm_b_lo); }
+  }
+  if (warp == 1) {     // one warp of EACH CTA of the pair takes part in the paired allocation
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(NCOLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();               // reconverge every warp before the .aligned cluster barrier
+  cluster_sync_all();            // the peer's barriers are initialised before anything can arrive on them
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): own image's A tile + own half of the B tile, signalled on the leader's full barrier =====
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int tile = pair_id; tile < total_tiles; tile += num_pairs) {
+        const int co0 = (tile % n_co) * BLOCK_N;
+        int t = tile / n_co;
+        const int tw = t % p.tiles_w; t /= p.tiles_w;
+        const int th = t % p.tiles_h; const int np = t / p.tiles_h;
+        const int n = min(2 * np + (int)rank, p.N - 1);           // odd batch: the peer of the last pair re-reads the last image (masked later)
+        const int h0 = th * TC_TH, w0 = tw * TC_TW;
+        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+          const int s = g % STAGES;
+          mbar_wait(smem_u32(&empty_bar[s]), ((g / STAGES) & 1) ^ 1);
+          const int tap = kb / cin_chunks, cc = kb - tap * cin_chunks;
+          const int r = tap / p.taps_w, sx = tap - r * p.taps_w;
+          const int hh = h0 * p.stride + (r - half) * p.dil, ww = w0 * p.stride + (sx - half) * p.dil;
+          uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+          const uint32_t bar = smem_u32(&full_bar[s]);
+          if (leader) mbar_expect_tx(bar, 2 * STAGE_BYTES);       // both CTAs' bytes land on this barrier
+          else mbar_arrive_cluster(bar, 0);
+          tma_load_4d_pair(smem_u32(st), &tm_a_hi, bar, cc * TC_BLOCK_K, ww, hh, n);
+          tma_load_2d_pair(smem_u32(st + NSPLIT * A_BYTES), &tm_b_hi, bar, kb * TC_BLOCK_K, co0 + (int)rank * HALF_N);
+          if (NSPLIT == 2) {
+            tma_load_4d_pair(smem_u32(st + A_BYTES), &tm_a_lo, bar, cc * TC_BLOCK_K, ww, hh, n);
+            tma_load_2d_pair(smem_u32(st + 2 * A_BYTES + B_BYTES), &tm_b_lo, bar, kb * TC_BLOCK_K, co0 + (int)rank * HALF_N);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one thread of the leader CTA drives both SMs' tensor cores =====
+    if (leader && lane == 0) {
+      uint32_t g = 0;
+      int it = 0;
+      for (int tile = pair_id; tile < total_tiles; tile += num_pairs, ++it) {
+        const int buf = it & 1;
+        mbar_wait(smem_u32(&acc_empty[buf]), ((it >> 1) & 1) ^ 1);      // the epilogues of BOTH CTAs have drained this accumulator
+        tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)(buf * BLOCK_N);
+        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+          const int s = g % STAGES;
+          mbar_wait(smem_u32(&full_bar[s]), (g / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + (size_t)s * STAGE_BYTES);
+          const uint64_t a_hi = make_kmajor_desc<TC_BLOCK_K>(st);
+          const uint64_t b_hi = make_kmajor_desc<TC_BLOCK_K>(st + NSPLIT * A_BYTES);
+          const uint64_t a_lo = make_kmajor_desc<TC_BLOCK_K>(st + A_BYTES);
+          const uint64_t b_lo = make_kmajor_desc<TC_BLOCK_K>(st + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
+            const uint64_t adv = (uint64_t)((k * 32) >> 4);
+            if (NPROD == 3) {
+              umma_bf16_pair(acc, a_hi + adv, b_lo + adv, IDESC, (kb | k) != 0);
+              umma_bf16_pair(acc, a_lo + adv, b_hi + adv, IDESC, 1);
+              umma_bf16_pair(acc, a_hi + adv, b_hi + adv, IDESC, 1);
+            } else {
+              umma_bf16_pair(acc, a_hi + adv, b_hi + adv, IDESC, (kb | k) != 0);
+            }
+          }
+          umma_commit_pair(smem_u32(&empty_bar[s]));          // frees the slot in both CTAs
+        }
+        umma_commit_pair(smem_u32(&acc_full[buf]));
+      }
+    }
+  } else {
+    // ===== epilogue warps (both CTAs): own 128 pixels x BLOCK_N channels from the local TMEM =====
+    // (same arithmetic as conv_tc_persistent_kernel's epilogue; kept separate until this kernel has run on hardware)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int it = 0;
+    for (int tile = pair_id; tile < total_tiles; tile += num_pairs, ++it) {
+      const int buf = it & 1;
+      const int co0 = (tile % n_co) * BLOCK_N;
+      int t = tile / n_co;
+      const int tw = t % p.tiles_w; t /= p.tiles_w;
+      const int th = t % p.tiles_h; const int np = t / p.tiles_h;
+      const int n = 2 * np + (int)rank;
+      const bool img_ok = n < p.N;
+      const int h = th * TC_TH + row / TC_TW, w = tw * TC_TW + row % TC_TW;
+      const bool ok = img_ok && h < p.H && w < p.W;
+      const size_t pix = ((size_t)(img_ok ? n : 0) * p.H + (ok ? h : 0)) * p.W + (ok ? w : 0);
+      const int sp = ((img_ok ? n : 0) * p.tiles_h + th) * p.tiles_w + tw;
+      float* o = p.out + pix * p.Cout + co0;
+      const float* ad = p.addend ? p.addend + pix * p.Cout + co0 : nullptr;
+      mbar_wait(smem_u32(&acc_full[buf]), (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        float4 adv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          adv[j] = (ad && ok) ? __ldg(reinterpret_cast<const float4*>(ad + c * 32) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BLOCK_N + c * 32), v);
+        if (p.ep_scale) {
+          const float4* sc = reinterpret_cast<const float4*>(p.ep_scale + co0 + c * 32);
+          const float4* sh = reinterpret_cast<const float4*>(p.ep_shift + co0 + c * 32);
+          uint32_t hp[16], lp[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 a = __ldg(sc + j), b = __ldg(sh + j);
+            float4 f = make_float4(fmaf(__uint_as_float(v[4 * j]), a.x, b.x) + adv[j].x, fmaf(__uint_as_float(v[4 * j + 1]), a.y, b.y) + adv[j].y,
+                                   fmaf(__uint_as_float(v[4 * j + 2]), a.z, b.z) + adv[j].z, fmaf(__uint_as_float(v[4 * j + 3]), a.w, b.w) + adv[j].w);
+            if (p.ep_relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f); }
+            if (ok && p.out) reinterpret_cast<float4*>(o + c * 32)[j] = f;
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(f.x), h1 = __float2bfloat16_rn(f.y), h2 = __float2bfloat16_rn(f.z), h3 = __float2bfloat16_rn(f.w);
+            hp[2 * j] = pack_bf16x2(h0, h1); hp[2 * j + 1] = pack_bf16x2(h2, h3);
+            lp[2 * j] = pack_bf16x2(__float2bfloat16_rn(f.x - __bfloat162float(h0)), __float2bfloat16_rn(f.y - __bfloat162float(h1)));
+            lp[2 * j + 1] = pack_bf16x2(__float2bfloat16_rn(f.z - __bfloat162float(h2)), __float2bfloat16_rn(f.w - __bfloat162float(h3)));
+          }
+          if (ok && p.out_hi) {
+            uint4* oh = reinterpret_cast<uint4*>(p.out_hi + pix * p.Cout + co0 + c * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) oh[j] = make_uint4(hp[4 * j], hp[4 * j + 1], hp[4 * j + 2], hp[4 * j + 3]);
+            if (p.out_lo) {
+              uint4* ol = reinterpret_cast<uint4*>(p.out_lo + pix * p.Cout + co0 + c * 32);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) ol[j] = make_uint4(lp[4 * j], lp[4 * j + 1], lp[4 * j + 2], lp[4 * j + 3]);
+            }
+          }
+        } else if (ok) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            reinterpret_cast<float4*>(o + c * 32)[j] =
+                make_float4(__uint_as_float(v[4 * j]) + adv[j].x, __uint_as_float(v[4 * j + 1]) + adv[j].y,
+                            __uint_as_float(v[4 * j + 2]) + adv[j].z, __uint_as_float(v[4 * j + 3]) + adv[j].w);
+        }
+        if (p.bn_partial) {
+          float a[32], b[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { a[j] = ok ? __uint_as_float(v[j]) : 0.f; b[j] = a[j] * a[j]; }
+          warp_colsum32(a, lane);
+          warp_colsum32(b, lane);
+          s_part[buf][0][q][c * 32 + lane] = a[0];
+          s_part[buf][1][q][c * 32 + lane] = b[0];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(smem_u32(&acc_empty[buf]), 0);     // 4 warps x 2 CTAs release the leader's MMA thread
+      if (p.bn_partial) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (img_ok) {
+          for (int e = threadIdx.x - 64; e < BLOCK_N; e += 128) {
+            const float s0 = s_part[buf][0][0][e] + s_part[buf][0][1][e] + s_part[buf][0][2][e] + s_part[buf][0][3][e];
+            const float s1 = s_part[buf][1][0][e] + s_part[buf][1][1][e] + s_part[buf][1][2][e] + s_part[buf][1][3][e];
+            p.bn_partial[(size_t)sp * p.Cout + co0 + e] = s0;
+            p.bn_partial[((size_t)n_sp + sp) * p.Cout + co0 + e] = s1;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();            // neither CTA frees its half of the paired TMEM while the other still uses the pair
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(NCOLS));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ weight gradient
 // dW[co][tap][ci] = sum_pixels dY[pixel][co] * X[pixel + offset(tap)][ci]  as a tcgen05 GEMM with the PIXELS as the K
 // dimension.  Both operands are the same NHWC bf16 planes the forward reads, consumed as MN-MAJOR UMMA operands
@@ -1073,6 +1342,32 @@ static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUt
   return 0;
 }
 
+// CTA-pair tiles (EXPERIMENTAL, see conv_tc_pair_kernel): DDN_TC_2CTA=1 -> 256 pixels x 256 channels for convs with
+// Cout % 256 == 0; DDN_TC_2CTA=2 -> additionally 256 x 128 for Cout % 128 == 0.  0 / unset: never used.
+static int tc_pair_mode() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DDN_TC_2CTA"); v = (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0; }
+  return tc_persistent_enabled() ? v : 0;
+}
+
+template <int BLOCK_N, int NPROD>
+static int launch_tc_pair(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                          const TcConvParams& p, cudaStream_t st) {
+  constexpr int NSPLIT = NPROD == 3 ? 2 : 1;
+  constexpr int STAGE_BYTES = NSPLIT * (TC_A_BYTES + (BLOCK_N / 2) * TC_BLOCK_K * 2);
+  constexpr int STAGES = (192 * 1024) / STAGE_BYTES >= 8 ? 8 : (192 * 1024) / STAGE_BYTES;
+  const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
+  static bool configured = false;
+  if (!configured) {
+    DDN_CUDA(cudaFuncSetAttribute(conv_tc_pair_kernel<BLOCK_N, NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int total = ((p.N + 1) / 2) * p.tiles_h * p.tiles_w * (p.Cout / BLOCK_N);
+  const int pairs = std::min(total, num_sms() / 2);
+  DDN_LAUNCH((conv_tc_pair_kernel<BLOCK_N, NPROD>), 2 * pairs, TC_THREADS, smem, st, a_hi, a_lo, b_hi, b_lo, p);   // clusters of 2
+  return 0;
+}
+
 // 256-wide tiles (persistent kernel only; opt-in with DDN_TC_N256=1): one A tile feeds twice the output channels and k-blocks
 // of 32 (64-byte swizzle rows) keep 4 pipeline stages.  Measured neutral on B200 (profiles/r1_tile_n256_ab.json: the
 // 128-wide kernel is not limited by shared-memory operand reads, and 256-wide tiles quantise worse over 148 SMs), so the
@@ -1111,8 +1406,9 @@ int tc_conv_planes(TcPlanes in, const float* w_oihw, const TcPlanes* wpk, float*
     DDN_LAUNCH(pack_weights_tc_kernel, wblocks, 256, 0, st, w_oihw, ph, pl, Cout, Cin, k, dgrad, want_lo);
     b_hi = ph; b_lo = pl;
   }
-  const int block_n = (gout % 256 == 0 && tc_wide_tiles_enabled()) ? 256 : gout % 128 == 0 ? 128 : 64;
-  const int bk = block_n == 256 ? 32 : TC_BLOCK_K;
+  const int pair_n = (tc_pair_mode() >= 1 && gout % 256 == 0) ? 256 : (tc_pair_mode() == 2 && gout % 128 == 0) ? 128 : 0;
+  const int block_n = pair_n ? pair_n / 2 : (gout % 256 == 0 && tc_wide_tiles_enabled()) ? 256 : gout % 128 == 0 ? 128 : 64;
+  const int bk = (!pair_n && block_n == 256) ? 32 : TC_BLOCK_K;     // pair mode: block_n = weight rows each CTA of the pair stages
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   DDN_TRY(make_act_map(&ma_hi, in.hi, N, H, W, gin, TC_TH, stride, bk));
   DDN_TRY(make_act_map(&ma_lo, want_lo ? in.lo : in.hi, N, H, W, gin, TC_TH, stride, bk));
@@ -1132,6 +1428,10 @@ int tc_conv_planes(TcPlanes in, const float* w_oihw, const TcPlanes* wpk, float*
     DDN_CHECK_ARG(out != nullptr, "conv output pointer is null");
   }
   ProfScope ps(dgrad ? PROF_CONV_DGRAD_TC : PROF_CONV_FWD_TC, fl, st);   // times the MMA kernel only
+  if (pair_n) {
+    if (want_lo) return pair_n == 256 ? launch_tc_pair<256, 3>(ma_hi, ma_lo, mb_hi, mb_lo, p, st) : launch_tc_pair<128, 3>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);
+    return pair_n == 256 ? launch_tc_pair<256, 1>(ma_hi, ma_lo, mb_hi, mb_lo, p, st) : launch_tc_pair<128, 1>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);
+  }
   if (want_lo) {
     if (block_n == 256) return launch_tc_persistent<256, 3, 32>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);
     if (block_n == 128) return launch_tc<128, 3>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);
