@@ -5,8 +5,8 @@ ONE kernel launch over the flat parameter / gradient arrays of ``Resnet34_8s`` (
     loss.backward(); optimizer.step()
 
 ``param_groups[0]['lr']`` is honoured every step, so the reference's ``adjust_learning_rate`` (training.py:544-558: x0.9
-every 250 iterations) works unchanged.  ``state_dict()`` / ``load_state_dict()`` round-trip the two moment arrays and the
-step count.  ``grad_scale`` lets a data-parallel run fold the 1/world of the gradient all-reduce into the update.
+every 250 iterations) works unchanged.  ``state_dict()`` / ``load_state_dict()`` speak torch.optim.Adam's own format, so the
+reference's ``NNNNNN.pth.opt`` files (training.py:509-511) resume here and ours resume in torch.optim.Adam.  ``grad_scale`` lets a data-parallel run fold the 1/world of the gradient all-reduce into the update.
 """
 import torch
 
@@ -52,11 +52,64 @@ class FusedAdam(object):
                                     float(g["weight_decay"]), float(grad_scale), N.stream_ptr()))
         self.fcn.mark_parameters_changed()      # the kernel wrote through a raw pointer: invalidate the weight-pack cache
 
+    # ---- optimizer checkpoints: the reference saves `optimizer.state_dict()` next to every model file
+    # (training.py:509-511, NNNNNN.pth.opt) and reloads it to resume (training.py:147-150), so the state is exchanged in
+    # torch.optim.Adam's own format: per-parameter `exp_avg` / `exp_avg_sq` / `step`, parameters numbered in
+    # `dcn.parameters()` order.  Files written by the reference load here, files written here load into torch.optim.Adam.
+    def _offsets(self, flat):
+        base, es = flat.data_ptr(), flat.element_size()
+        return [((q.data_ptr() - base) // es, q.numel()) for q in self.param_groups[0]["params"]]
+
     def state_dict(self):
-        return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
-                "param_groups": [{k: v for k, v in self.param_groups[0].items() if k != "params"}]}
+        g = {k: v for k, v in self.param_groups[0].items() if k != "params"}
+        g.setdefault("amsgrad", False); g.setdefault("maximize", False)
+        params = self.param_groups[0]["params"]
+        g["params"] = list(range(len(params)))
+        state = {}
+        if self.exp_avg is not None:
+            flat = self.fcn.flat_parameters
+            for i, (q, (off, n)) in enumerate(zip(params, self._offsets(flat))):
+                state[i] = {"step": torch.tensor(float(self.step_count)),
+                            "exp_avg": self.exp_avg[off:off + n].view(q.shape).clone(),
+                            "exp_avg_sq": self.exp_avg_sq[off:off + n].view(q.shape).clone()}
+        return {"state": state, "param_groups": [g]}
 
     def load_state_dict(self, sd):
-        self.step_count = int(sd["step"])
-        self.exp_avg, self.exp_avg_sq = sd["exp_avg"], sd["exp_avg_sq"]
-        self.param_groups[0].update(sd["param_groups"][0])
+        if "state" not in sd:      # the flat layout this class wrote before it spoke torch's format
+            self.step_count = int(sd["step"])
+            self.exp_avg, self.exp_avg_sq = sd["exp_avg"], sd["exp_avg_sq"]
+            self.param_groups[0].update(sd["param_groups"][0])
+            return
+        groups = sd["param_groups"]
+        if len(groups) != 1:
+            raise ValueError("FusedAdam.load_state_dict: expected one parameter group (training.py:133-145 builds one), got %d" % len(groups))
+        params = self.param_groups[0]["params"]
+        ids = list(groups[0]["params"])
+        if len(ids) != len(params):
+            raise ValueError("FusedAdam.load_state_dict: checkpoint has %d parameters, the network has %d" % (len(ids), len(params)))
+        if groups[0].get("amsgrad", False):
+            raise ValueError("FusedAdam.load_state_dict: amsgrad state is not supported")
+        for k in ("lr", "betas", "eps", "weight_decay"):
+            if k in groups[0]:
+                self.param_groups[0][k] = tuple(groups[0][k]) if k == "betas" else groups[0][k]
+        state = sd["state"]
+        if not state:
+            self.step_count, self.exp_avg, self.exp_avg_sq = 0, None, None
+            return
+        flat = self.fcn.flat_parameters
+        self._ensure_state(flat)
+        self.exp_avg.zero_(); self.exp_avg_sq.zero_()
+        steps = set()
+        for pid, q, (off, n) in zip(ids, params, self._offsets(flat)):
+            st = state.get(pid, state.get(str(pid)))
+            if st is None:
+                raise ValueError("FusedAdam.load_state_dict: no state for parameter %r" % (pid,))
+            if tuple(st["exp_avg"].shape) != tuple(q.shape):
+                raise ValueError("FusedAdam.load_state_dict: parameter %r has shape %s in the checkpoint, %s here"
+                                 % (pid, tuple(st["exp_avg"].shape), tuple(q.shape)))
+            self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
+            self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+            steps.add(int(float(st["step"])))
+        if len(steps) != 1:
+            raise ValueError("FusedAdam.load_state_dict: parameters disagree on the step count (%s); one fused update cannot resume that" % sorted(steps))
+        self.step_count = steps.pop()

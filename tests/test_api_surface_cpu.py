@@ -73,3 +73,40 @@ def test_clip_pixel_and_precision_switch():
     assert dcn.clip_pixel_to_image_size_and_round((10.4, 20.6)) == [10, 21]
     with pytest.raises(Exception):
         pdc_b200.set_default_precision("fp64")
+
+
+def test_fused_adam_state_dict_is_torch_adam_compatible():
+    """training.py:509-511 saves `optimizer.state_dict()` as NNNNNN.pth.opt and :147-150 resumes from it: a file written by
+    torch.optim.Adam must load into FusedAdam (moments land at the right offsets of the flat arrays) and the other way round."""
+    torch.manual_seed(0)
+    net = pdc_b200.Resnet34_8s(num_classes=3)                      # CPU: only state handling is exercised, no kernel
+    params = list(net.parameters())
+    ref = torch.optim.Adam(params, lr=1e-4, weight_decay=1e-4)
+    for _ in range(2):
+        for q in params:
+            q.grad = torch.randn_like(q) * 1e-3
+        ref.step()
+    sd = ref.state_dict()
+    opt = pdc_b200.FusedAdam(net, lr=1.0, weight_decay=0.0)
+    opt.load_state_dict(sd)
+    assert opt.step_count == 2 and opt.param_groups[0]["lr"] == 1e-4 and opt.param_groups[0]["weight_decay"] == 1e-4
+    flat = net.flat_parameters
+    for i, q in enumerate(params):
+        off = (q.data_ptr() - flat.data_ptr()) // 4
+        assert torch.equal(opt.exp_avg[off:off + q.numel()].view(q.shape), sd["state"][i]["exp_avg"])
+        assert torch.equal(opt.exp_avg_sq[off:off + q.numel()].view(q.shape), sd["state"][i]["exp_avg_sq"])
+    # alignment padding between tensors carries no state
+    covered = sum(q.numel() for q in params)
+    assert float(opt.exp_avg.abs().sum()) == pytest.approx(float(sum(sd["state"][i]["exp_avg"].abs().sum() for i in range(len(params)))), rel=1e-5)
+    assert flat.numel() >= covered
+    # and back: our checkpoint resumes a stock torch.optim.Adam
+    back = torch.optim.Adam(params, lr=1.0)
+    back.load_state_dict(opt.state_dict())
+    sb = back.state_dict()
+    assert sb["param_groups"][0]["lr"] == 1e-4 and len(sb["state"]) == len(params)
+    for i in range(len(params)):
+        assert torch.equal(sb["state"][i]["exp_avg"], sd["state"][i]["exp_avg"]) and float(sb["state"][i]["step"]) == 2.0
+    # a checkpoint for another network is refused
+    bad = {"state": {}, "param_groups": [dict(sd["param_groups"][0], params=[0, 1, 2])]}
+    with pytest.raises(ValueError):
+        opt.load_state_dict(bad)

@@ -260,8 +260,17 @@ def test_fused_adam_matches_torch_adam():
         ref.step(); ours.step()
         a, b = net_a.flat_parameters, net_b.flat_parameters
         assert float((a - b).abs().max()) <= 2e-7 + 1e-6 * float(a.abs().max()), it
-    sd = ours.state_dict()
-    assert sd["step"] == 3 and sd["exp_avg"].shape == net_b.flat_parameters.shape
+    # checkpoints are exchanged in torch.optim.Adam's own format (training.py:509-511 writes NNNNNN.pth.opt)
+    sd, ref_sd = ours.state_dict(), ref.state_dict()
+    assert len(sd["state"]) == len(ref_sd["state"]) == len(list(net_b.parameters()))
+    for i in (0, 7, len(sd["state"]) - 1):
+        assert float(sd["state"][i]["step"]) == 3.0 and sd["state"][i]["exp_avg"].shape == ref_sd["state"][i]["exp_avg"].shape
+        for k in ("exp_avg", "exp_avg_sq"):
+            a, b = sd["state"][i][k], ref_sd["state"][i][k]
+            assert float((a - b).abs().max()) <= 1e-3 * float(b.abs().max()) + 1e-20, (i, k)
+    resumed = pdc_b200.FusedAdam(net_b, lr=1.0)
+    resumed.load_state_dict(ref_sd)
+    assert resumed.step_count == 3 and resumed.param_groups[0]["lr"] == ref.param_groups[0]["lr"]
 
 
 def test_weight_pack_cache_follows_parameter_updates():
