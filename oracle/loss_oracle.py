@@ -4,8 +4,8 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
 ``--impl reference`` leg may import this file; the product never does.
 
 Two independent restatements of the same reference source (which is Python-2 and
-cannot be imported: TabError at pixelwise_contrastive_loss.py:8, print statements
-in loss_composer.py:28):
+cannot be imported as it lies: TabError at pixelwise_contrastive_loss.py:8, print
+statements in loss_composer.py:28):
 
 * ``Torch*``  -- line-by-line Python-3 torch restatement (autograd provides the
   reference gradient).  ``/`` on ints is ``//`` (py2 semantics) wherever the
@@ -29,9 +29,14 @@ Reference lines followed (dense_correspondence/loss_functions/):
   dataset/dense_correspondence_dataset_masked.py:209-223  empty_tensor / is_empty sentinel
   dataset/spartan_dataset_masked.py:31-36                 SpartanDatasetDataType
 
-Parity status: the reference ships no golden vectors for this path (SURVEY.md 8c);
-the torch and numpy restatements pin each other and tests/golden/ freezes their
-agreed outputs.
+Parity status: PINNED to the executed reference.  The reference ships no golden vectors
+for this path, so oracle/build_ref.py makes the reference's own files
+importable (line-anchored py2->py3 patches, written to the git-ignored oracle/_ref/) and
+tests/test_oracle_ref_cpu.py requires the torch restatement below to be BIT-EQUAL to the
+executed reference (values, hard-negative counts, autograd gradients, every public method
+and composer branch, the non-match sampler and the reprojection match finder); the numpy
+restatement agrees to 1e-6; tests/golden/loss_*.npz hold the executed reference's outputs
+(oracle/make_golden.py).
 """
 import numpy as np
 import torch

@@ -5,8 +5,9 @@ Run in the BUILD CONTAINER only (needs /root/reference):   python oracle/make_go
 For every backbone case the REAL reference module (loaded unmodified by oracle/ref_loader.py)
 and the oracle restatement are run on the same seeded weights and inputs and must agree
 bit-for-bit (forward, running statistics, parameter gradients); the reference's outputs are what
-is stored.  For the loss (whose reference source is Python 2 and cannot be executed) the torch
-and numpy restatements must agree to 1e-6 and the torch values are stored.
+is stored.  For the loss the reference's OWN source is executed (oracle/build_ref.py: the Python-2 files with a short
+list of line-anchored py2->py3 patches, written to the git-ignored oracle/_ref/): its outputs and autograd gradients
+are what is stored, and the torch restatement must equal them bit-for-bit and the numpy one to 1e-6.
 """
 import os
 import sys
@@ -19,6 +20,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "pytorch-dense-correspondence_b200"))
 
 from oracle import loss_oracle as LO            # noqa: E402
+from oracle import build_ref                    # noqa: E402
 from oracle import ref_loader                   # noqa: E402
 from oracle.resnet34_8s_oracle import seeded_oracle, process_network_output  # noqa: E402
 import synthetic                                # noqa: E402
@@ -85,10 +87,18 @@ def loss_case(name, D, H, W, Nm, k_masked, k_bg, n_blind, cfg_over, seed):
         xa = torch.randint(0, P, (n_blind,), generator=g); xb = torch.randint(0, P, (n_blind,), generator=g)
     else:
         xa = xb = LO.empty_tensor()
-    pcl = LO.TorchPixelwiseContrastiveLoss([H, W], cfg)
-    mt = torch.tensor([LO.SpartanDatasetDataType.SINGLE_OBJECT_WITHIN_SCENE])
-    five = LO.get_loss(pcl, mt, pa, pb, ma, mb, na_m, nb_m, na_b, nb_b, xa, xb)
+    # the executed reference (oracle/_ref) produces the stored values ...
+    ref = build_ref.load()
+    mt = torch.tensor([ref.dataset.SpartanDatasetDataType.SINGLE_OBJECT_WITHIN_SCENE])
+    five = ref.composer.get_loss(ref.pcl.PixelwiseContrastiveLoss([H, W], dict(cfg)), mt, pa, pb, ma, mb, na_m, nb_m, na_b, nb_b, xa, xb)
     five[0].reshape(()).backward()
+    # ... and the torch restatement must reproduce them bit-for-bit (same ops, same order)
+    A2 = A.detach().clone().requires_grad_(); B2 = Bt.detach().clone().requires_grad_()
+    five_o = LO.get_loss(LO.TorchPixelwiseContrastiveLoss([H, W], dict(cfg)), mt, process_network_output(A2, 1, D, H, W),
+                         process_network_output(B2, 1, D, H, W), ma, mb, na_m, nb_m, na_b, nb_b, xa, xb)
+    five_o[0].reshape(()).backward()
+    assert [float(t) for t in five_o] == [float(t) for t in five], name
+    assert torch.equal(A2.grad, A.grad) and torch.equal(B2.grad, Bt.grad), name
     idx = dict(matches_a=ma.numpy(), matches_b=mb.numpy(), masked_a=na_m.numpy(), masked_b=nb_m.numpy(),
                background_a=na_b.numpy(), background_b=nb_b.numpy(),
                blind_a=xa.numpy(), blind_b=xb.numpy())
@@ -105,7 +115,8 @@ def loss_case(name, D, H, W, Nm, k_masked, k_bg, n_blind, cfg_over, seed):
 
 
 def train_step_case(name, D, B, H, W, Nm, Nn, seed):
-    """fwd(A), fwd(B), within-scene loss (mean over pairs), backward -- reference backbone + restated loss."""
+    """fwd(A), fwd(B), within-scene loss (mean over pairs), backward -- reference backbone + the loss restatement (which the
+    loss cases above and tests/test_oracle_ref_cpu.py pin bit-for-bit to the executed reference loss)."""
     oracle = seeded_oracle(D=D, seed=0)
     ref = ref_loader.reference_resnet34_8s(D, oracle.state_dict())
     ref.train()
@@ -127,7 +138,8 @@ def train_step_case(name, D, B, H, W, Nm, Nn, seed):
 
 
 if __name__ == "__main__":
-    assert ref_loader.reference_available(), "needs /root/reference"
+    assert ref_loader.reference_available() and build_ref.reference_available(), "needs /root/reference"
+    build_ref.build()
     os.makedirs(GOLD, exist_ok=True)
     backbone_case("backbone_small_d3", D=3, B=2, H=64, W=96, seed_data=11)
     backbone_case("backbone_small_d16", D=16, B=1, H=48, W=64, seed_data=12)
