@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define DDN_ABI_VERSION 1
+#define DDN_ABI_VERSION 2
 
 enum {
   DDN_OK = 0,
@@ -74,24 +74,42 @@ int64_t ddn_resnet34_8s_buffer_count(void);
  *
  * x  [B,3,H,W] fp32 NCHW (already mean/std normalised), y [B,D,H,W] fp32 NCHW contiguous.
  * H, W multiples of 8 (the trunk runs at H/8 x W/8).  1 <= D <= 32.
- * training != 0: BatchNorm uses the statistics of THIS call's B images (biased variance) and updates
+ * mode DDN_MODE_TRAIN: BatchNorm uses the statistics of THIS call's images (biased variance) and updates
  *   running_mean/var in `buffers` with `momentum` and the unbiased variance, exactly like
- *   nn.BatchNorm2d; the activations needed by backward are kept in `workspace`.
- * training == 0: BatchNorm uses `buffers`; nothing is kept.
- * The same `workspace` (untouched in between) must be handed to ddn_resnet34_8s_backward, which
- * OVERWRITES grads[0 .. param_count) with dL/dparams for the cotangent dy [B,D,H,W].
- * dx may be NULL (the reference never differentiates the image).
+ *   nn.BatchNorm2d in train(); the activations needed by backward are kept in `workspace`.
+ * mode DDN_MODE_INFER: BatchNorm uses `buffers` (folded into the conv epilogues); nothing is kept.
+ * mode DDN_MODE_EVAL_SAVE: BatchNorm uses `buffers` (frozen statistics) and the activations are kept, so that
+ *   ddn_resnet34_8s_backward can differentiate an eval()-mode network like autograd does for the reference.
+ * bn_groups G (1 or 2): the batch is G consecutive groups of B/G images, each normalised by its OWN batch
+ *   statistics -- G = 2 runs the reference's two forward calls of a step (image A batch, image B batch:
+ *   dense_correspondence/training/training.py:329-333) as one launch sequence; running statistics are updated
+ *   group 0 first, then group 1, as the two calls would.
+ * The same `workspace` (untouched in between) must be handed to ddn_resnet34_8s_backward (same mode / bn_groups),
+ * which OVERWRITES grads[0 .. param_count) with dL/dparams for the cotangent dy [B,D,H,W].
+ * on_bucket (may be NULL) is called on the HOST, in order, each time a contiguous range of `grads` is final --
+ *   i.e. right after the last kernel writing grads[offset, offset+numel) has been enqueued on `stream` -- so that a
+ *   data-parallel caller can start the all-reduce of that range while the rest of the backward still runs
+ *   (4 ranges, last layers first; ddn_resnet34_8s_grad_buckets lists them).
  * ------------------------------------------------------------------------------------------ */
-size_t ddn_resnet34_8s_workspace_bytes(int B, int H, int W, int D, int training, int precision);
+enum { DDN_MODE_INFER = 0, DDN_MODE_TRAIN = 1, DDN_MODE_EVAL_SAVE = 2 };
+
+size_t ddn_resnet34_8s_workspace_bytes(int B, int H, int W, int D, int mode, int precision);
 
 int ddn_resnet34_8s_forward(const float* x, const float* params, float* buffers, float* y,
                             void* workspace, size_t workspace_bytes,
                             int B, int H, int W, int D,
-                            int training, float momentum, float eps, int precision, void* stream);
+                            int mode, int bn_groups, float momentum, float eps, int precision, void* stream);
+
+typedef void (*ddn_grad_bucket_fn)(void* user, int bucket, int64_t offset, int64_t numel);
 
 int ddn_resnet34_8s_backward(const float* dy, const float* params, float* grads,
                              void* workspace, size_t workspace_bytes,
-                             int B, int H, int W, int D, float eps, int precision, void* stream);
+                             int B, int H, int W, int D, int mode, int bn_groups, float eps, int precision,
+                             ddn_grad_bucket_fn on_bucket, void* user, void* stream);
+
+/* offsets[0..3] = first element of gradient bucket 0..3 (in completion order), offsets[4] = param_count; returns 4.
+ * Bucket i covers [offsets[i], offsets[i-1]) for i > 0 and [offsets[0], param_count) for i = 0. */
+int ddn_resnet34_8s_grad_buckets(int D, int64_t* offsets, int cap);
 
 /* Optional cache of the tensor-core weight packs (bf16 hi/lo, forward and data-gradient layouts of every conv).
  * The caller owns `cache` (ddn_resnet34_8s_weight_cache_bytes(D) bytes of device memory) and bumps `version` whenever the

@@ -9,11 +9,11 @@ raises if that library is missing -- there is no CPU / PyTorch fallback.
 from . import _native
 from .resnet_dilated import Resnet34_8s, set_default_precision
 from .dense_correspondence_network import DenseCorrespondenceNetwork
-from .pixelwise_contrastive_loss import PixelwiseContrastiveLoss
+from .pixelwise_contrastive_loss import PixelwiseContrastiveLoss, DEFAULT_LOSS_CONFIG
 from . import loss_composer
 from .loss_composer import SpartanDatasetDataType
 from .fused_adam import FusedAdam
 from . import ops, synthetic, data_parallel, sampling
 
 __all__ = ["Resnet34_8s", "DenseCorrespondenceNetwork", "PixelwiseContrastiveLoss", "loss_composer",
-           "SpartanDatasetDataType", "set_default_precision", "FusedAdam", "ops", "synthetic", "data_parallel", "sampling"]
+           "SpartanDatasetDataType", "DEFAULT_LOSS_CONFIG", "set_default_precision", "FusedAdam", "ops", "synthetic", "data_parallel", "sampling"]

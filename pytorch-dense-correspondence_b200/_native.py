@@ -11,6 +11,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libddn_b200.so")
 
 PRECISION_FP32_SIMT, PRECISION_BF16X3, PRECISION_BF16 = 0, 1, 2
+MODE_INFER, MODE_TRAIN, MODE_EVAL_SAVE = 0, 1, 2
+GRAD_BUCKET_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64)
 TERM_MATCH, TERM_HINGE, TERM_HINGE_INV = 0, 1, 2
 TERM_PIXEL_WEIGHT = 1
 MAX_TERMS = 8
@@ -50,8 +52,9 @@ _SIGNATURES = {
     "ddn_resnet34_8s_workspace_bytes": (sz, [i32, i32, i32, i32, i32, i32]),
     "ddn_resnet34_8s_weight_cache_bytes": (sz, [i32]),
     "ddn_resnet34_8s_set_weight_cache": (i32, [vp, sz, vp, ctypes.c_uint64, i32]),
-    "ddn_resnet34_8s_forward": (i32, [vp, vp, vp, vp, vp, sz, i32, i32, i32, i32, i32, f32, f32, i32, vp]),
-    "ddn_resnet34_8s_backward": (i32, [vp, vp, vp, vp, sz, i32, i32, i32, i32, f32, i32, vp]),
+    "ddn_resnet34_8s_forward": (i32, [vp, vp, vp, vp, vp, sz, i32, i32, i32, i32, i32, i32, f32, f32, i32, vp]),
+    "ddn_resnet34_8s_backward": (i32, [vp, vp, vp, vp, sz, i32, i32, i32, i32, i32, i32, f32, i32, GRAD_BUCKET_FN, vp, vp]),
+    "ddn_resnet34_8s_grad_buckets": (i32, [i32, ctypes.POINTER(i64), i32]),
     "ddn_contrastive_terms_forward": (i32, [vp, vp, i64, i64, i64, i32, i64, i32, i32, ctypes.POINTER(LossTerm), i32, vp, vp, vp]),
     "ddn_contrastive_terms_backward": (i32, [vp, vp, i64, i64, i64, i32, i64, i32, i32, ctypes.POINTER(LossTerm), i32,
                                              vp, vp, vp, vp, vp]),
@@ -99,7 +102,7 @@ def _load():
         fn = getattr(lib, name)      # AttributeError here == header/library mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.ddn_abi_version() != 1:
+    if lib.ddn_abi_version() != 2:
         raise ImportError("libddn_b200.so ABI version mismatch")
     return lib
 
@@ -145,6 +148,17 @@ def buffer_table():
     arr = (TensorEntry * n)()
     lib.ddn_resnet34_8s_buffer_table(arr, n)
     return [(e.name.decode(), tuple(e.shape[:e.ndim]), int(e.offset), int(e.numel)) for e in arr]
+
+
+def grad_buckets(D):
+    """[(offset, numel)] of the 4 gradient buckets in the order the backward completes them (last layers first)."""
+    arr = (i64 * 5)()
+    n = lib.ddn_resnet34_8s_grad_buckets(D, arr, 5)
+    ends = [int(arr[4])] + [int(arr[i]) for i in range(n - 1)]
+    return [(int(arr[i]), ends[i] - int(arr[i])) for i in range(n)]
+
+
+NO_BUCKET_CALLBACK = ctypes.cast(None, GRAD_BUCKET_FN)
 
 
 def profile_read():

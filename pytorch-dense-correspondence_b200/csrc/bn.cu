@@ -1,10 +1,15 @@
-// BatchNorm2d (+residual, +ReLU) forward/backward on NHWC fp32 viewed as [M][C], and the stem's fused
+// BatchNorm2d (+residual, +ReLU) forward/backward on NHWC tensors viewed as [M][C], and the stem's fused
 // BN + ReLU + MaxPool(3,2,1).  All HBM-bound elementwise / column-reduction kernels.
 //
 // Reference semantics: nn.BatchNorm2d / nn.ReLU(inplace) / nn.MaxPool2d(3,2,1) as wired by
 // PSD/vision/torchvision/models/resnet.py:53-69 (BasicBlock.forward) and :231-236 (stem):
 // training = batch mean and BIASED variance over (N,H,W), eps inside the sqrt, running statistics updated
 // with momentum and the UNBIASED variance; eval = running statistics.
+//
+// Byte diet of round 2 (tensor-core modes): activations exist ONLY as bf16 hi/lo operand planes (x ~= hi + lo, 16
+// mantissa bits -- what every conv reads anyway); the residual add reads the planes, the ReLU mask of a BatchNorm without
+// residual is recomputed from its own input, and column statistics are finalized by the last CTA of the kernel that
+// produced them (bn_stats.cuh) instead of by a second launch.  G > 1: per-group batch statistics (pair-batched step).
 #include "conv.cuh"
 
 namespace ddn {
@@ -24,24 +29,10 @@ __device__ __forceinline__ void store_split4(__nv_bfloat16* hi, __nv_bfloat16* l
     reinterpret_cast<uint2*>(lo)[i4] = l2;
   }
 }
-
-static inline int bn_rows_per_iter(int C) { return BN_THREADS / (C / 4); }
-
-int bn_partial_blocks(int64_t M, int C) {
-  int rpi = bn_rows_per_iter(C);
-  int64_t target = (int64_t)num_sms() * 4;
-  int64_t iters = std::max<int64_t>(4, ceil_div(M, (int64_t)rpi * target));
-  return (int)ceil_div(M, (int64_t)rpi * iters);
+__device__ __forceinline__ float4 bf16x4_to_float4(uint2 h) {
+  return make_float4(__uint_as_float(h.x << 16), __uint_as_float(h.x & 0xffff0000u), __uint_as_float(h.y << 16),
+                     __uint_as_float(h.y & 0xffff0000u));
 }
-static inline int64_t bn_rows_per_block(int64_t M, int C) {
-  int rpi = bn_rows_per_iter(C);
-  int64_t target = (int64_t)num_sms() * 4;
-  int64_t iters = std::max<int64_t>(4, ceil_div(M, (int64_t)rpi * target));
-  return (int64_t)rpi * iters;
-}
-
-// column sums of v0(x) and v1(x) over a row chunk -> partial[0][blk][C], partial[1][blk][C]
-// MODE 0: (x, x^2)      MODE 1: (g, g*xhat) with g = dy * (y > 0 if relu)
 // 4 packed bf16 values > 0 ?  (sign bit clear and not +/-0)
 __device__ __forceinline__ void mask_from_bf16x4(uint2 h, float4& g) {
   if ((h.x & 0x8000u) || !(h.x & 0x7fffu)) g.x = 0.f;
@@ -50,111 +41,109 @@ __device__ __forceinline__ void mask_from_bf16x4(uint2 h, float4& g) {
   if ((h.y & 0x80000000u) || !(h.y & 0x7fff0000u)) g.w = 0.f;
 }
 
+size_t bn_accum_bytes(int C) { return align_up(sizeof(double) * BN_MAX_GROUPS * 2 * (size_t)C, 256) + 256; }
+BnAccum bn_accum_at(void* base, int C) {
+  BnAccum a;
+  a.acc = reinterpret_cast<double*>(base);
+  a.ticket = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(base) + align_up(sizeof(double) * BN_MAX_GROUPS * 2 * (size_t)C, 256));
+  return a;
+}
+
+static inline int bn_rows_per_iter(int C) { return BN_THREADS / (C / 4); }
+// blocks per group: ~2 CTAs per SM over all groups, at least 4 row iterations per block
+static int bn_colsum_blocks(int64_t Mg, int C, int G) {
+  const int rpi = bn_rows_per_iter(C);
+  const int64_t target = std::max<int64_t>(1, (int64_t)num_sms() * 2 / G);
+  const int64_t iters = std::max<int64_t>(4, ceil_div(Mg, (int64_t)rpi * target));
+  return (int)ceil_div(Mg, (int64_t)rpi * iters);
+}
+static int64_t bn_colsum_rows_per_block(int64_t Mg, int C, int G) {
+  const int rpi = bn_rows_per_iter(C);
+  const int64_t target = std::max<int64_t>(1, (int64_t)num_sms() * 2 / G);
+  const int64_t iters = std::max<int64_t>(4, ceil_div(Mg, (int64_t)rpi * target));
+  return (int64_t)rpi * iters;
+}
+
+struct BnColsumArgs {
+  const float* x; const float* dy; const float* y; const __nv_bfloat16* y_hi;
+  const float* mean; const float* invstd; const float* gamma; const float* beta;   // [G][C] statistics (MODE 1)
+  int64_t Mg; int C; int64_t rows_per_block; int relu;
+};
+
+// column sums of v0, v1 over this block's rows of group blockIdx.y, added into the fp64 accumulator; the last CTA finalizes
+// MODE 0: (x, x^2) -> BatchNorm statistics      MODE 1: (g, g*xhat) with g = dy * (y > 0 if relu) -> dgamma / dbeta / sums
 template <int MODE>
 __global__ void __launch_bounds__(BN_THREADS)
-bn_colsum_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ y,
-                 const __nv_bfloat16* __restrict__ y_hi,
-                 const float* __restrict__ mean, const float* __restrict__ invstd,
-                 int64_t M, int C, int64_t rows_per_block, int relu, float* __restrict__ partial) {
-  const int q = C >> 2;
+bn_colsum_kernel(BnColsumArgs a, BnFwdFinal ff, BnBwdFinal fb) {
+  const int C = a.C, q = C >> 2;
   const int cq = threadIdx.x % q, rr = threadIdx.x / q, rpi = BN_THREADS / q;
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
-  const int64_t r1 = min(M, r0 + rows_per_block);
+  const int g = blockIdx.y;
+  const int64_t r0 = (int64_t)g * a.Mg + (int64_t)blockIdx.x * a.rows_per_block;
+  const int64_t r1 = min((int64_t)(g + 1) * a.Mg, r0 + a.rows_per_block);
   float4 s0 = make_float4(0, 0, 0, 0), s1 = make_float4(0, 0, 0, 0);
-  float4 mu = make_float4(0, 0, 0, 0), is = make_float4(1, 1, 1, 1);
+  float4 mu = make_float4(0, 0, 0, 0), is = make_float4(1, 1, 1, 1), sc = is, be = mu;
+  const bool recompute_mask = MODE == 1 && a.relu && !a.y && !a.y_hi;
   if (MODE == 1) {
-    mu = reinterpret_cast<const float4*>(mean)[cq];
-    is = reinterpret_cast<const float4*>(invstd)[cq];
+    mu = reinterpret_cast<const float4*>(a.mean + (size_t)g * C)[cq];
+    is = reinterpret_cast<const float4*>(a.invstd + (size_t)g * C)[cq];
+    if (recompute_mask) {
+      const float4 ga = reinterpret_cast<const float4*>(a.gamma)[cq];
+      be = reinterpret_cast<const float4*>(a.beta)[cq];
+      sc = make_float4(ga.x * is.x, ga.y * is.y, ga.z * is.z, ga.w * is.w);
+    }
   }
   for (int64_t r = r0 + rr; r < r1; r += rpi) {
-    float4 v = __ldg(reinterpret_cast<const float4*>(x + r * C) + cq);
+    float4 v = __ldg(reinterpret_cast<const float4*>(a.x + r * C) + cq);
     if (MODE == 0) {
       s0.x += v.x; s0.y += v.y; s0.z += v.z; s0.w += v.w;
       s1.x = fmaf(v.x, v.x, s1.x); s1.y = fmaf(v.y, v.y, s1.y); s1.z = fmaf(v.z, v.z, s1.z); s1.w = fmaf(v.w, v.w, s1.w);
     } else {
-      float4 g = __ldg(reinterpret_cast<const float4*>(dy + r * C) + cq);
-      if (relu) {
-        if (y_hi) {     // the bf16 "hi" plane of y has y's sign and zero-ness: half the bytes of the fp32 copy
-          mask_from_bf16x4(__ldg(reinterpret_cast<const uint2*>(y_hi + r * C) + cq), g);
-        } else {
-          float4 o = __ldg(reinterpret_cast<const float4*>(y + r * C) + cq);
-          g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+      float4 gr = __ldg(reinterpret_cast<const float4*>(a.dy + r * C) + cq);
+      if (a.relu) {
+        if (a.y_hi) {     // the bf16 "hi" plane of y has y's sign and zero-ness
+          mask_from_bf16x4(__ldg(reinterpret_cast<const uint2*>(a.y_hi + r * C) + cq), gr);
+        } else if (a.y) {
+          float4 o = __ldg(reinterpret_cast<const float4*>(a.y + r * C) + cq);
+          gr.x = o.x > 0.f ? gr.x : 0.f; gr.y = o.y > 0.f ? gr.y : 0.f; gr.z = o.z > 0.f ? gr.z : 0.f; gr.w = o.w > 0.f ? gr.w : 0.f;
+        } else {          // no residual in the forward: y > 0  <=>  bn(x) > 0, same fmaf as bn_apply_kernel
+          if (!(fmaf(v.x - mu.x, sc.x, be.x) > 0.f)) gr.x = 0.f;
+          if (!(fmaf(v.y - mu.y, sc.y, be.y) > 0.f)) gr.y = 0.f;
+          if (!(fmaf(v.z - mu.z, sc.z, be.z) > 0.f)) gr.z = 0.f;
+          if (!(fmaf(v.w - mu.w, sc.w, be.w) > 0.f)) gr.w = 0.f;
         }
       }
-      s0.x += g.x; s0.y += g.y; s0.z += g.z; s0.w += g.w;
-      s1.x = fmaf(g.x, (v.x - mu.x) * is.x, s1.x); s1.y = fmaf(g.y, (v.y - mu.y) * is.y, s1.y);
-      s1.z = fmaf(g.z, (v.z - mu.z) * is.z, s1.z); s1.w = fmaf(g.w, (v.w - mu.w) * is.w, s1.w);
+      s0.x += gr.x; s0.y += gr.y; s0.z += gr.z; s0.w += gr.w;
+      s1.x = fmaf(gr.x, (v.x - mu.x) * is.x, s1.x); s1.y = fmaf(gr.y, (v.y - mu.y) * is.y, s1.y);
+      s1.z = fmaf(gr.z, (v.z - mu.z) * is.z, s1.z); s1.w = fmaf(gr.w, (v.w - mu.w) * is.w, s1.w);
     }
   }
   __shared__ float4 sh0[BN_THREADS], sh1[BN_THREADS];
+  __shared__ int s_last;
   sh0[threadIdx.x] = s0; sh1[threadIdx.x] = s1;
   __syncthreads();
+  double* acc = MODE == 0 ? ff.a.acc : fb.a.acc;
   if (rr == 0) {
     for (int k = 1; k < rpi; ++k) {
-      float4 a = sh0[k * q + cq], b = sh1[k * q + cq];
-      s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
-      s1.x += b.x; s1.y += b.y; s1.z += b.z; s1.w += b.w;
+      float4 u = sh0[k * q + cq], w = sh1[k * q + cq];
+      s0.x += u.x; s0.y += u.y; s0.z += u.z; s0.w += u.w;
+      s1.x += w.x; s1.y += w.y; s1.z += w.z; s1.w += w.w;
     }
-    int64_t nblk = gridDim.x;
-    reinterpret_cast<float4*>(partial + (int64_t)blockIdx.x * C)[cq] = s0;
-    reinterpret_cast<float4*>(partial + (nblk + blockIdx.x) * C)[cq] = s1;
+    double* p0 = acc + (size_t)(g * 2) * C + (cq << 2);
+    double* p1 = p0 + C;
+    red_add_f64(p0, (double)s0.x); red_add_f64(p0 + 1, (double)s0.y); red_add_f64(p0 + 2, (double)s0.z); red_add_f64(p0 + 3, (double)s0.w);
+    red_add_f64(p1, (double)s1.x); red_add_f64(p1 + 1, (double)s1.y); red_add_f64(p1 + 2, (double)s1.z); red_add_f64(p1 + 3, (double)s1.w);
   }
-}
-
-// Column sums of the per-block partials in fp64.  Block = 4 channels (one 16-byte segment per partial row) x 64 slices;
-// every thread walks nblk/64 rows with 8 independent loads in flight, so even ~1200 partial rows are ~5 dependent rounds
-// (these kernels are pure load latency: 2-128 CTAs, a few KB to a few MB of partials).
-constexpr int FIN_CH = 4, FIN_SLICES = 64;
-__device__ __forceinline__ void reduce_partials(const float* __restrict__ partial, int nblk, int C, int c, int slice,
-                                                double& s, double& ss) {
-  double s0 = 0, s1 = 0, s2 = 0, s3 = 0, q0 = 0, q1 = 0, q2 = 0, q3 = 0;
-  if (c < C) {
-    const float* ps = partial + c;
-    const float* pq = partial + (int64_t)nblk * C + c;
-    int b = slice;
-    for (; b + 3 * FIN_SLICES < nblk; b += 4 * FIN_SLICES) {
-      float a0 = __ldg(ps + (int64_t)b * C), a1 = __ldg(ps + (int64_t)(b + FIN_SLICES) * C);
-      float a2 = __ldg(ps + (int64_t)(b + 2 * FIN_SLICES) * C), a3 = __ldg(ps + (int64_t)(b + 3 * FIN_SLICES) * C);
-      float b0 = __ldg(pq + (int64_t)b * C), b1 = __ldg(pq + (int64_t)(b + FIN_SLICES) * C);
-      float b2 = __ldg(pq + (int64_t)(b + 2 * FIN_SLICES) * C), b3 = __ldg(pq + (int64_t)(b + 3 * FIN_SLICES) * C);
-      s0 += (double)a0; s1 += (double)a1; s2 += (double)a2; s3 += (double)a3;
-      q0 += (double)b0; q1 += (double)b1; q2 += (double)b2; q3 += (double)b3;
+  unsigned int* ticket = MODE == 0 ? ff.a.ticket : fb.a.ticket;
+  const bool last = bn_last_cta(ticket, gridDim.x * gridDim.y, threadIdx.x == 0, &s_last, [] { __syncthreads(); });
+  if (last) {
+    for (int c = threadIdx.x; c < C; c += BN_THREADS) {
+      if (MODE == 0) bn_fwd_finalize_channel(ff, c);
+      else bn_bwd_finalize_channel(fb, c);
     }
-    for (; b < nblk; b += FIN_SLICES) { s0 += (double)__ldg(ps + (int64_t)b * C); q0 += (double)__ldg(pq + (int64_t)b * C); }
-  }
-  s = (s0 + s1) + (s2 + s3); ss = (q0 + q1) + (q2 + q3);
-  __shared__ double sh[2][FIN_SLICES][FIN_CH];
-  const int ch = threadIdx.x & (FIN_CH - 1);
-  sh[0][slice][ch] = s; sh[1][slice][ch] = ss;
-  __syncthreads();
-  if (slice == 0) {
-#pragma unroll 8
-    for (int k = 1; k < FIN_SLICES; ++k) { s += sh[0][k][ch]; ss += sh[1][k][ch]; }
   }
 }
 
-__global__ void __launch_bounds__(256)
-bn_stats_finalize_kernel(const float* __restrict__ partial, int nblk, int64_t M, int C,
-                         float* __restrict__ mean, float* __restrict__ invstd,
-                         float* __restrict__ running_mean, float* __restrict__ running_var,
-                         float momentum, float eps) {
-  const int c = blockIdx.x * FIN_CH + (threadIdx.x & (FIN_CH - 1)), slice = threadIdx.x / FIN_CH;
-  double s, ss;
-  reduce_partials(partial, nblk, C, c, slice, s, ss);
-  if (slice != 0 || c >= C) return;
-  double mu = s / (double)M;
-  double var = ss / (double)M - mu * mu;
-  if (var < 0) var = 0;
-  mean[c] = (float)mu;
-  invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
-  if (running_mean) {
-    double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
-    running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * mu);
-    running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unbiased);
-  }
-}
-
-// eval-mode BatchNorm as one multiply-add per element: y = x * scale + shift
+// eval-mode BN folded to one multiply-add per element: y = x * scale + shift
 __global__ void bn_fold_kernel(const float* __restrict__ rm, const float* __restrict__ rv, const float* __restrict__ gamma,
                                const float* __restrict__ beta, int C, float eps, float* __restrict__ scale, float* __restrict__ shift) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -164,84 +153,114 @@ __global__ void bn_fold_kernel(const float* __restrict__ rm, const float* __rest
   shift[c] = fmaf(-rm[c], sc, beta[c]);
 }
 
-__global__ void bn_eval_stats_kernel(const float* __restrict__ rm, const float* __restrict__ rv, int C, float eps,
+__global__ void bn_eval_stats_kernel(const float* __restrict__ rm, const float* __restrict__ rv, int C, int G, float eps,
                                      float* __restrict__ mean, float* __restrict__ invstd) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  mean[c] = rm[c];
-  invstd[c] = 1.0f / sqrtf(rv[c] + eps);
+  const float m = rm[c], is = 1.0f / sqrtf(rv[c] + eps);
+  for (int g = 0; g < G; ++g) { mean[g * C + c] = m; invstd[g * C + c] = is; }
+}
+
+constexpr int BN_EVAL_MAX_SEGS = 40;
+struct BnEvalSegs { BnEvalSeg s[BN_EVAL_MAX_SEGS]; int n; };
+// every BatchNorm of the network in one launch: blockIdx.y = BatchNorm, stats = [G][C] mean then [G][C] invstd
+__global__ void bn_eval_stats_all_kernel(const float* __restrict__ buffers, float* __restrict__ stats, BnEvalSegs segs, int G, float eps) {
+  const BnEvalSeg sg = segs.s[blockIdx.y];
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < sg.C; c += gridDim.x * blockDim.x) {
+    const float m = buffers[sg.rm_off + c], is = 1.0f / sqrtf(buffers[sg.rv_off + c] + eps);
+    for (int g = 0; g < G; ++g) {
+      stats[sg.stat_off + (size_t)g * sg.C + c] = m;
+      stats[sg.stat_off + (size_t)(G + g) * sg.C + c] = is;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(BN_THREADS)
 bn_apply_kernel(BnApplyArgs a) {
-  extern __shared__ float sm[];   // scale[C], mean[C], beta[C] (+ same for residual BN)
-  float* sc = sm; float* mu = sm + a.C; float* be = sm + 2 * a.C;
-  float* rsc = sm + 3 * a.C; float* rmu = sm + 4 * a.C; float* rbe = sm + 5 * a.C;
+  extern __shared__ float sm[];   // per group: scale[C], mean[C], beta[C] (+ the same three of the residual's BatchNorm)
+  const int C = a.C, G = a.G;
   const bool res_bn = a.r && a.rmean;
-  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
-    sc[c] = a.gamma[c] * a.invstd[c]; mu[c] = a.mean[c]; be[c] = a.beta[c];
-    if (res_bn) { rsc[c] = a.rgamma[c] * a.rinvstd[c]; rmu[c] = a.rmean[c]; rbe[c] = a.rbeta[c]; }
+  const int per_g = (res_bn ? 6 : 3) * C;
+  for (int i = threadIdx.x; i < G * C; i += blockDim.x) {
+    const int g = i / C, c = i - g * C;
+    float* b = sm + g * per_g;
+    b[c] = a.gamma[c] * a.invstd[i]; b[C + c] = a.mean[i]; b[2 * C + c] = a.beta[c];
+    if (res_bn) { b[3 * C + c] = a.rgamma[c] * a.rinvstd[i]; b[4 * C + c] = a.rmean[i]; b[5 * C + c] = a.rbeta[c]; }
   }
   __syncthreads();
-  const int q = a.C >> 2;
+  const int q = C >> 2;
   const int64_t total = a.M * q;
+  const int64_t per_group = (a.M / G) * q;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int c = (int)(i % q) << 2;
+    const int c = (int)(i % q) << 2;
+    const float* b = sm + (G > 1 ? (int)(i / per_group) : 0) * per_g;
+    const float* sc = b; const float* mu = b + C; const float* be = b + 2 * C;
     float4 v = __ldg(reinterpret_cast<const float4*>(a.x) + i);
     v.x = fmaf(v.x - mu[c], sc[c], be[c]); v.y = fmaf(v.y - mu[c + 1], sc[c + 1], be[c + 1]);
     v.z = fmaf(v.z - mu[c + 2], sc[c + 2], be[c + 2]); v.w = fmaf(v.w - mu[c + 3], sc[c + 3], be[c + 3]);
     if (a.r) {
       float4 r = __ldg(reinterpret_cast<const float4*>(a.r) + i);
       if (res_bn) {
+        const float* rsc = b + 3 * C; const float* rmu = b + 4 * C; const float* rbe = b + 5 * C;
         r.x = fmaf(r.x - rmu[c], rsc[c], rbe[c]); r.y = fmaf(r.y - rmu[c + 1], rsc[c + 1], rbe[c + 1]);
         r.z = fmaf(r.z - rmu[c + 2], rsc[c + 2], rbe[c + 2]); r.w = fmaf(r.w - rmu[c + 3], rsc[c + 3], rbe[c + 3]);
       }
       v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    } else if (a.r_hi) {       // identity residual from the operand planes: r = hi + lo
+      float4 r = bf16x4_to_float4(__ldg(reinterpret_cast<const uint2*>(a.r_hi) + i));
+      if (a.r_lo) {
+        const float4 l = bf16x4_to_float4(__ldg(reinterpret_cast<const uint2*>(a.r_lo) + i));
+        r.x += l.x; r.y += l.y; r.z += l.z; r.w += l.w;
+      }
+      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
     }
     if (a.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-    reinterpret_cast<float4*>(a.y)[i] = v;
+    if (a.y) reinterpret_cast<float4*>(a.y)[i] = v;
     if (a.hi) store_split4(a.hi, a.lo, i, v);
   }
 }
 
-__global__ void __launch_bounds__(256)
-bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C,
-                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int c = blockIdx.x * FIN_CH + (threadIdx.x & (FIN_CH - 1)), slice = threadIdx.x / FIN_CH;
-  double s, ss;
-  reduce_partials(partial, nblk, C, c, slice, s, ss);
-  if (slice != 0 || c >= C) return;
-  dbeta[c] = (float)s;
-  dgamma[c] = (float)ss;
-}
-
-// dx = gamma*invstd*(g - dbeta/M - xhat*dgamma/M)  (training)   |   gamma*invstd*g  (eval)
+// dx = gamma*invstd*(g - dbeta_g/Mg - xhat*dgamma_g/Mg)  (training)   |   gamma*invstd*g  (eval: frozen statistics)
 __global__ void __launch_bounds__(BN_THREADS)
 bn_bwd_apply_kernel(BnBwdArgs a) {
-  extern __shared__ float sm[];
-  float* k1 = sm; float* mu = sm + a.C; float* is = sm + 2 * a.C; float* mb = sm + 3 * a.C; float* mg = sm + 4 * a.C;
-  const float invM = (float)(1.0 / (double)a.M);
-  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
-    k1[c] = a.gamma[c] * a.invstd[c]; mu[c] = a.mean[c]; is[c] = a.invstd[c];
-    mb[c] = a.training ? a.dbeta[c] * invM : 0.f;
-    mg[c] = a.training ? a.dgamma[c] * invM : 0.f;
+  extern __shared__ float sm[];   // per group: k1[C], mean[C], invstd[C], dbeta/M[C], dgamma/M[C], scale[C], beta[C]
+  const int C = a.C, G = a.G;
+  const int64_t Mg = a.M / G;
+  const float invM = (float)(1.0 / (double)Mg);
+  const bool recompute_mask = a.relu && !a.y && !a.y_hi;
+  for (int i = threadIdx.x; i < G * C; i += blockDim.x) {
+    const int g = i / C, c = i - g * C;
+    float* b = sm + g * 7 * C;
+    b[c] = a.gamma[c] * a.invstd[i]; b[C + c] = a.mean[i]; b[2 * C + c] = a.invstd[i];
+    b[3 * C + c] = a.training ? a.sums[(g * 2) * C + c] * invM : 0.f;
+    b[4 * C + c] = a.training ? a.sums[(g * 2 + 1) * C + c] * invM : 0.f;
+    b[5 * C + c] = a.gamma[c] * a.invstd[i]; b[6 * C + c] = a.beta ? a.beta[c] : 0.f;
   }
   __syncthreads();
-  const int q = a.C >> 2;
+  const int q = C >> 2;
   const int64_t total = a.M * q;
+  const int64_t per_group = Mg * q;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int c = (int)(i % q) << 2;
+    const int c = (int)(i % q) << 2;
+    const float* b = sm + (G > 1 ? (int)(i / per_group) : 0) * 7 * C;
+    const float* k1 = b; const float* mu = b + C; const float* is = b + 2 * C; const float* mb = b + 3 * C; const float* mg = b + 4 * C;
     float4 g = __ldg(reinterpret_cast<const float4*>(a.dy) + i);
+    float4 v = __ldg(reinterpret_cast<const float4*>(a.x) + i);
     if (a.relu) {
       if (a.y_hi) {
         mask_from_bf16x4(__ldg(reinterpret_cast<const uint2*>(a.y_hi) + i), g);
-      } else {
+      } else if (a.y) {
         float4 o = __ldg(reinterpret_cast<const float4*>(a.y) + i);
         g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+      } else if (recompute_mask) {
+        const float* sc = b + 5 * C; const float* be = b + 6 * C;
+        if (!(fmaf(v.x - mu[c], sc[c], be[c]) > 0.f)) g.x = 0.f;
+        if (!(fmaf(v.y - mu[c + 1], sc[c + 1], be[c + 1]) > 0.f)) g.y = 0.f;
+        if (!(fmaf(v.z - mu[c + 2], sc[c + 2], be[c + 2]) > 0.f)) g.z = 0.f;
+        if (!(fmaf(v.w - mu[c + 3], sc[c + 3], be[c + 3]) > 0.f)) g.w = 0.f;
       }
     }
     if (a.g_out) reinterpret_cast<float4*>(a.g_out)[i] = g;
-    float4 v = __ldg(reinterpret_cast<const float4*>(a.x) + i);
     float4 d;
     d.x = k1[c] * (g.x - mb[c] - (v.x - mu[c]) * is[c] * mg[c]);
     d.y = k1[c + 1] * (g.y - mb[c + 1] - (v.y - mu[c + 1]) * is[c + 1] * mg[c + 1]);
@@ -258,14 +277,15 @@ __global__ void __launch_bounds__(256)
 stem_bn_relu_pool_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
                          const float* __restrict__ gamma, const float* __restrict__ beta,
                          float* __restrict__ y, uint8_t* __restrict__ argmax, __nv_bfloat16* __restrict__ y_hi,
-                         __nv_bfloat16* __restrict__ y_lo, int N, int Hc, int Wc, int C, int Hp, int Wp) {
+                         __nv_bfloat16* __restrict__ y_lo, int N, int Hc, int Wc, int C, int Hp, int Wp, int imgs_per_group) {
   const int q = C >> 2;
   const int64_t total = (int64_t)N * Hp * Wp * q;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % q) << 2; int64_t t = i / q;
     int wp = (int)(t % Wp); t /= Wp;
     int hp = (int)(t % Hp); int n = (int)(t / Hp);
-    float4 mu = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(invstd + c);
+    const int so = (n / imgs_per_group) * C + c;
+    float4 mu = *reinterpret_cast<const float4*>(mean + so), is = *reinterpret_cast<const float4*>(invstd + so);
     float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
     float4 sc = make_float4(ga.x * is.x, ga.y * is.y, ga.z * is.z, ga.w * is.w);
     float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
@@ -288,7 +308,7 @@ stem_bn_relu_pool_kernel(const float* __restrict__ x, const float* __restrict__ 
         if (v.w > best.w) { best.w = v.w; arg.w = k; }
       }
     }
-    reinterpret_cast<float4*>(y)[i] = best;
+    if (y) reinterpret_cast<float4*>(y)[i] = best;
     reinterpret_cast<uchar4*>(argmax)[i] = arg;
     if (y_hi) store_split4(y_hi, y_lo, i, best);
   }
@@ -299,7 +319,7 @@ __global__ void __launch_bounds__(256)
 stem_pool_relu_bwd_kernel(const float* __restrict__ dyp, const uint8_t* __restrict__ argmax, const float* __restrict__ x,
                           const float* __restrict__ mean, const float* __restrict__ invstd,
                           const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ g,
-                          int N, int Hc, int Wc, int C, int Hp, int Wp) {
+                          int N, int Hc, int Wc, int C, int Hp, int Wp, int imgs_per_group) {
   const int q = C >> 2;
   const int64_t total = (int64_t)N * Hc * Wc * q;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -328,7 +348,8 @@ stem_pool_relu_bwd_kernel(const float* __restrict__ dyp, const uint8_t* __restri
         if (am.w == k) acc.w += d.w;
       }
     }
-    float4 mu = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(invstd + c);
+    const int so = (n / imgs_per_group) * C + c;
+    float4 mu = *reinterpret_cast<const float4*>(mean + so), is = *reinterpret_cast<const float4*>(invstd + so);
     float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
     float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
     if (!(fmaf(v.x - mu.x, ga.x * is.x, be.x) > 0.f)) acc.x = 0.f;
@@ -340,33 +361,37 @@ stem_pool_relu_bwd_kernel(const float* __restrict__ dyp, const uint8_t* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
-static int check_c(int C) {
+static int check_c(int C, int G, int64_t M) {
   DDN_CHECK_ARG(C >= 4 && C % 4 == 0 && (C / 4) <= BN_THREADS && BN_THREADS % (C / 4) == 0,
                 "BatchNorm kernels need C in {4..1024} with 256 %% (C/4) == 0 (got %d)", C);
+  DDN_CHECK_ARG(G >= 1 && G <= BN_MAX_GROUPS && M % G == 0, "BatchNorm groups: need 1 <= G <= %d dividing the row count", BN_MAX_GROUPS);
   return 0;
 }
 static int ew_blocks(int64_t total) { return (int)std::min<int64_t>(ceil_div(total, BN_THREADS), (int64_t)num_sms() * 8); }
 
-int launch_bn_stats(const float* x, int64_t M, int C, float* partial, float* mean, float* invstd,
+int launch_bn_stats(const float* x, int64_t M, int C, int G, BnAccum acc, float* mean, float* invstd,
                     float* running_mean, float* running_var, float momentum, float eps, cudaStream_t st) {
-  DDN_TRY(check_c(C));
-  int nblk = bn_partial_blocks(M, C);
-  DDN_LAUNCH(bn_colsum_kernel<0>, nblk, BN_THREADS, 0, st, x, nullptr, nullptr, nullptr, nullptr, nullptr, M, C,
-             bn_rows_per_block(M, C), 0, partial);
-  DDN_LAUNCH(bn_stats_finalize_kernel, (int)ceil_div(C, FIN_CH), 256, 0, st, partial, nblk, M, C, mean, invstd,
-             running_mean, running_var, momentum, eps);
+  DDN_TRY(check_c(C, G, M));
+  const int64_t Mg = M / G;
+  BnColsumArgs a = {x, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, Mg, C, bn_colsum_rows_per_block(Mg, C, G), 0};
+  BnFwdFinal ff = {acc, mean, invstd, running_mean, running_var, Mg, G, C, momentum, eps};
+  BnBwdFinal fb = {};
+  dim3 grid((unsigned)bn_colsum_blocks(Mg, C, G), (unsigned)G);
+  DDN_LAUNCH(bn_colsum_kernel<0>, grid, BN_THREADS, 0, st, a, ff, fb);
   return 0;
 }
 
-int launch_bn_stats_finalize(const float* partial, int nblk, int64_t M, int C, float* mean, float* invstd,
-                             float* running_mean, float* running_var, float momentum, float eps, cudaStream_t st) {
-  DDN_LAUNCH(bn_stats_finalize_kernel, (int)ceil_div(C, FIN_CH), 256, 0, st, partial, nblk, M, C, mean, invstd,
-             running_mean, running_var, momentum, eps);
+int launch_bn_eval_stats(const float* rm, const float* rv, int C, int G, float eps, float* mean, float* invstd, cudaStream_t st) {
+  DDN_LAUNCH(bn_eval_stats_kernel, (int)ceil_div(C, 128), 128, 0, st, rm, rv, C, G, eps, mean, invstd);
   return 0;
 }
 
-int launch_bn_eval_stats(const float* rm, const float* rv, int C, float eps, float* mean, float* invstd, cudaStream_t st) {
-  DDN_LAUNCH(bn_eval_stats_kernel, (int)ceil_div(C, 128), 128, 0, st, rm, rv, C, eps, mean, invstd);
+int launch_bn_eval_stats_all(const float* buffers, float* stats_base, const BnEvalSeg* segs, int n_segs, int G, float eps, cudaStream_t st) {
+  DDN_CHECK_ARG(n_segs >= 1 && n_segs <= BN_EVAL_MAX_SEGS, "too many BatchNorm segments");
+  BnEvalSegs s; s.n = n_segs;
+  for (int i = 0; i < n_segs; ++i) s.s[i] = segs[i];
+  dim3 grid(2, (unsigned)n_segs);
+  DDN_LAUNCH(bn_eval_stats_all_kernel, grid, 256, 0, st, buffers, stats_base, s, G, eps);
   return 0;
 }
 
@@ -377,37 +402,43 @@ int launch_bn_fold(const float* rm, const float* rv, const float* gamma, const f
 }
 
 int launch_bn_apply(const BnApplyArgs& a, cudaStream_t st) {
-  DDN_TRY(check_c(a.C));
-  DDN_LAUNCH(bn_apply_kernel, ew_blocks(a.M * (a.C / 4)), BN_THREADS, 6 * a.C * sizeof(float), st, a);
+  DDN_TRY(check_c(a.C, a.G, a.M));
+  const size_t smem = (size_t)a.G * ((a.r && a.rmean) ? 6 : 3) * a.C * sizeof(float);
+  DDN_LAUNCH(bn_apply_kernel, ew_blocks(a.M * (a.C / 4)), BN_THREADS, smem, st, a);
   return 0;
 }
 
 int launch_bn_backward(const BnBwdArgs& a, cudaStream_t st) {
-  DDN_TRY(check_c(a.C));
-  int nblk = bn_partial_blocks(a.M, a.C);
-  DDN_LAUNCH(bn_colsum_kernel<1>, nblk, BN_THREADS, 0, st, a.x, a.dy, a.y, a.y_hi, a.mean, a.invstd, a.M, a.C,
-             bn_rows_per_block(a.M, a.C), a.relu, a.partial);
-  DDN_LAUNCH(bn_bwd_finalize_kernel, (int)ceil_div(a.C, FIN_CH), 256, 0, st, a.partial, nblk, a.C, a.dgamma, a.dbeta);
-  DDN_LAUNCH(bn_bwd_apply_kernel, ew_blocks(a.M * (a.C / 4)), BN_THREADS, 5 * a.C * sizeof(float), st, a);
+  DDN_TRY(check_c(a.C, a.G, a.M));
+  const int64_t Mg = a.M / a.G;
+  BnColsumArgs ca = {a.x, a.dy, a.y, a.y_hi, a.mean, a.invstd, a.gamma, a.beta, Mg, a.C, bn_colsum_rows_per_block(Mg, a.C, a.G), a.relu};
+  DDN_CHECK_ARG(!(a.relu && !a.y && !a.y_hi) || a.beta, "recomputing the ReLU mask needs beta");
+  BnFwdFinal ff = {};
+  BnBwdFinal fb = {a.acc, a.sums, a.dgamma, a.dbeta, a.G, a.C};
+  dim3 grid((unsigned)bn_colsum_blocks(Mg, a.C, a.G), (unsigned)a.G);
+  DDN_LAUNCH(bn_colsum_kernel<1>, grid, BN_THREADS, 0, st, ca, ff, fb);
+  const size_t smem = (size_t)a.G * 7 * a.C * sizeof(float);
+  DDN_LAUNCH(bn_bwd_apply_kernel, ew_blocks(a.M * (a.C / 4)), BN_THREADS, smem, st, a);
   return 0;
 }
 
 int launch_stem_bn_relu_pool(const float* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
                              float* y, uint8_t* argmax, __nv_bfloat16* y_hi, __nv_bfloat16* y_lo,
-                             int N, int Hc, int Wc, int C, cudaStream_t st) {
+                             int N, int Hc, int Wc, int C, int G, cudaStream_t st) {
   int Hp = (Hc - 1) / 2 + 1, Wp = (Wc - 1) / 2 + 1;
   int64_t total = (int64_t)N * Hp * Wp * (C / 4);
-  DDN_LAUNCH(stem_bn_relu_pool_kernel, ew_blocks(total), 256, 0, st, x, mean, invstd, gamma, beta, y, argmax, y_hi, y_lo, N, Hc, Wc, C, Hp, Wp);
+  DDN_LAUNCH(stem_bn_relu_pool_kernel, ew_blocks(total), 256, 0, st, x, mean, invstd, gamma, beta, y, argmax, y_hi, y_lo, N, Hc, Wc, C,
+             Hp, Wp, N / G);
   return 0;
 }
 
 int launch_stem_pool_relu_backward(const float* dy_pool, const uint8_t* argmax, const float* x, const float* mean,
                                    const float* invstd, const float* gamma, const float* beta, float* g,
-                                   int N, int Hc, int Wc, int C, cudaStream_t st) {
+                                   int N, int Hc, int Wc, int C, int G, cudaStream_t st) {
   int Hp = (Hc - 1) / 2 + 1, Wp = (Wc - 1) / 2 + 1;
   int64_t total = (int64_t)N * Hc * Wc * (C / 4);
   DDN_LAUNCH(stem_pool_relu_bwd_kernel, ew_blocks(total), 256, 0, st, dy_pool, argmax, x, mean, invstd, gamma, beta, g,
-             N, Hc, Wc, C, Hp, Wp);
+             N, Hc, Wc, C, Hp, Wp, N / G);
   return 0;
 }
 

@@ -18,10 +18,25 @@ __global__ void nchw_to_nhwc4_kernel(const float* __restrict__ x, float* __restr
   }
 }
 
+// 4 consecutive features: fp32, or reconstructed from the bf16 operand planes (feat = hi + lo) when feat == nullptr
+__device__ __forceinline__ float4 load_feat4(const float* feat, const __nv_bfloat16* hi, const __nv_bfloat16* lo, int64_t i4) {
+  if (feat) return __ldg(reinterpret_cast<const float4*>(feat) + i4);
+  const uint2 h = __ldg(reinterpret_cast<const uint2*>(hi) + i4);
+  float4 v = make_float4(__uint_as_float(h.x << 16), __uint_as_float(h.x & 0xffff0000u), __uint_as_float(h.y << 16),
+                         __uint_as_float(h.y & 0xffff0000u));
+  if (lo) {
+    const uint2 l = __ldg(reinterpret_cast<const uint2*>(lo) + i4);
+    v.x += __uint_as_float(l.x << 16); v.y += __uint_as_float(l.x & 0xffff0000u);
+    v.z += __uint_as_float(l.y << 16); v.w += __uint_as_float(l.y & 0xffff0000u);
+  }
+  return v;
+}
+
 // low[n][d][p] = bias[d] + sum_c feat[n][p][c] * w[d][c]; one warp per pixel, lanes split the channels
 template <int DM>
 __global__ void __launch_bounds__(256)
-fc_forward_kernel(const float* __restrict__ feat, const float* __restrict__ w, const float* __restrict__ bias,
+fc_forward_kernel(const float* __restrict__ feat, const __nv_bfloat16* __restrict__ feat_hi, const __nv_bfloat16* __restrict__ feat_lo,
+                  const float* __restrict__ w, const float* __restrict__ bias,
                   float* __restrict__ low, int64_t Mimg, int N, int C, int D) {
   extern __shared__ float ws[];   // [D][C]
   for (int i = threadIdx.x; i < D * C; i += blockDim.x) ws[i] = w[i];
@@ -33,9 +48,8 @@ fc_forward_kernel(const float* __restrict__ feat, const float* __restrict__ w, c
     float acc[DM];
 #pragma unroll
     for (int d = 0; d < DM; ++d) acc[d] = 0.f;
-    const float4* f = reinterpret_cast<const float4*>(feat + pix * C);
     for (int c4 = lane; c4 < (C >> 2); c4 += 32) {
-      float4 v = __ldg(f + c4);
+      const float4 v = load_feat4(feat, feat_hi, feat_lo, pix * (C >> 2) + c4);
 #pragma unroll
       for (int d = 0; d < DM; ++d) {
         if (d < D) {
@@ -84,7 +98,8 @@ fc_dgrad_kernel(const float* __restrict__ dlow, const float* __restrict__ w, flo
 // dw[d][c] = sum_{n,p} dlow[n][d][p]*feat[n][p][c];  dbias[d] = sum dlow.  Block = C threads-quads x pixel chunk.
 template <int DM>
 __global__ void __launch_bounds__(256)
-fc_wgrad_kernel(const float* __restrict__ dlow, const float* __restrict__ feat, float* __restrict__ dw,
+fc_wgrad_kernel(const float* __restrict__ dlow, const float* __restrict__ feat, const __nv_bfloat16* __restrict__ feat_hi,
+                const __nv_bfloat16* __restrict__ feat_lo, float* __restrict__ dw,
                 float* __restrict__ dbias, int64_t Mimg, int N, int C, int D, int pix_per_block) {
   const int64_t total = (int64_t)N * Mimg;
   const int64_t p0 = (int64_t)blockIdx.x * pix_per_block;
@@ -103,7 +118,12 @@ fc_wgrad_kernel(const float* __restrict__ dlow, const float* __restrict__ feat, 
     for (int k = 0; k < 2; ++k) {
       int c = threadIdx.x + k * 256;
       if (c < C) {
-        float f = __ldg(feat + pix * C + c);
+        float f;
+        if (feat) f = __ldg(feat + pix * C + c);
+        else {
+          f = __bfloat162float(feat_hi[pix * C + c]);
+          if (feat_lo) f += __bfloat162float(feat_lo[pix * C + c]);
+        }
 #pragma unroll
         for (int d = 0; d < DM; ++d) acc[k][d] = fmaf(g[d], f, acc[k][d]);
       }
@@ -216,20 +236,23 @@ int launch_nchw_to_nhwc4(const float* x, float* y, int N, int H, int W, cudaStre
     else { CALL(32); }                    \
   } while (0)
 
-int launch_fc_forward(const float* feat, const float* w, const float* bias, float* low, int64_t Mimg, int N, int C, int D, cudaStream_t st) {
+int launch_fc_forward(const float* feat, const __nv_bfloat16* feat_hi, const __nv_bfloat16* feat_lo, const float* w, const float* bias,
+                      float* low, int64_t Mimg, int N, int C, int D, cudaStream_t st) {
+  DDN_CHECK_ARG(feat || feat_hi, "fc: no feature tensor");
   DDN_CHECK_ARG(D >= 1 && D <= FC_MAXD && C % 4 == 0 && C <= 512, "fc: need 1<=D<=32, C%%4==0, C<=512");
   size_t smem = sizeof(float) * D * C;
   int blocks = (int)std::min<int64_t>(ceil_div((int64_t)N * Mimg, 8), (int64_t)num_sms() * 8);
 #define CALL(DM)                                                                                              \
   DDN_CUDA(cudaFuncSetAttribute(fc_forward_kernel<DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-  DDN_LAUNCH(fc_forward_kernel<DM>, blocks, 256, smem, st, feat, w, bias, low, Mimg, N, C, D)
+  DDN_LAUNCH(fc_forward_kernel<DM>, blocks, 256, smem, st, feat, feat_hi, feat_lo, w, bias, low, Mimg, N, C, D)
   FC_DISPATCH(D, CALL);
 #undef CALL
   return 0;
 }
 
-int launch_fc_backward(const float* dlow, const float* feat, const float* w, float* dfeat, float* dw, float* dbias,
-                       int64_t Mimg, int N, int C, int D, cudaStream_t st) {
+int launch_fc_backward(const float* dlow, const float* feat, const __nv_bfloat16* feat_hi, const __nv_bfloat16* feat_lo, const float* w,
+                       float* dfeat, float* dw, float* dbias, int64_t Mimg, int N, int C, int D, cudaStream_t st) {
+  DDN_CHECK_ARG(feat || feat_hi, "fc: no feature tensor");
   DDN_CHECK_ARG(D >= 1 && D <= FC_MAXD && C % 4 == 0 && C <= 512, "fc: need 1<=D<=32, C%%4==0, C<=512");
   size_t smem = sizeof(float) * D * C;
   int64_t total = (int64_t)N * Mimg;
@@ -242,7 +265,7 @@ int launch_fc_backward(const float* dlow, const float* feat, const float* w, flo
   DDN_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * D, st));
   int ppb = (int)std::max<int64_t>(16, ceil_div(total, (int64_t)num_sms() * 4));
   int blocks = (int)ceil_div(total, ppb);
-#define CALL(DM) DDN_LAUNCH(fc_wgrad_kernel<DM>, blocks, 256, 0, st, dlow, feat, dw, dbias, Mimg, N, C, D, ppb)
+#define CALL(DM) DDN_LAUNCH(fc_wgrad_kernel<DM>, blocks, 256, 0, st, dlow, feat, feat_hi, feat_lo, dw, dbias, Mimg, N, C, D, ppb)
   FC_DISPATCH(D, CALL);
 #undef CALL
   return 0;

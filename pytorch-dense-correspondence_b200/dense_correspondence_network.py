@@ -105,6 +105,22 @@ class DenseCorrespondenceNetwork(nn.Module):
             res = res / norm
         return res
 
+    def forward_pair(self, img_a, img_b):
+        """(image_a_pred, image_b_pred) = (self.forward(img_a), self.forward(img_b)) -- the two forward calls of a reference
+        training step (dense_correspondence/training/training.py:329-333) -- executed as ONE launch sequence over the
+        concatenated batch with two BatchNorm groups: each image batch is normalised by its own batch statistics and the
+        running statistics are updated A-then-B, exactly as the two calls would, but every kernel runs once on twice the
+        pixels (half the launches, better SM fill) and there is a single backward.  Opt-in: the reference API is two calls."""
+        if img_a.shape != img_b.shape:
+            raise ValueError("forward_pair needs two image batches of the same shape")
+        B = img_a.shape[0]
+        res = self.fcn(torch.cat([img_a, img_b], 0), bn_groups=2)
+        res_a, res_b = res[:B], res[B:]
+        if self._normalize:
+            res_a = res_a / torch.norm(res_a, 2, 1)
+            res_b = res_b / torch.norm(res_b, 2, 1)
+        return res_a, res_b
+
     def forward_single_image_tensor(self, img_tensor):
         """[3,H,W] -> [H,W,D] (net.py:265-299)."""
         assert len(img_tensor.shape) == 3

@@ -15,6 +15,18 @@ from . import _native as N
 from .contrastive_ops import Term, contrastive_terms
 
 
+# the reference's default loss configuration (config/dense_correspondence/training/training.yaml:51-61)
+DEFAULT_LOSS_CONFIG = {
+    "M_masked": 0.5, "M_background": 0.5, "M_pixel": 50,
+    "match_loss_weight": 1.0, "non_match_loss_weight": 1.0,
+    "use_l2_pixel_loss_on_masked_non_matches": False,
+    "use_l2_pixel_loss_on_background_non_matches": False,
+    "scale_by_hard_negatives": True,
+    "scale_by_hard_negatives_DIFFERENT_OBJECT": True,
+    "alpha_triplet": 0.1,
+}
+
+
 class PixelwiseContrastiveLoss(object):
 
     def __init__(self, image_shape, config=None):

@@ -42,29 +42,44 @@ class _Holder(nn.Module):
 
 
 class _Backbone(torch.autograd.Function):
+    """forward / backward of the whole backbone as ONE autograd node over the C ABI.
+
+    Parameter gradients are written by the library into one flat array and, by default, attached / accumulated into
+    ``p.grad`` by this function itself (every ``p.grad`` is a view of ``Resnet34_8s.flat_gradient``: the data-parallel
+    all-reduce and the fused optimizer see one buffer, and the second backward of a step is one flat add instead of 110
+    AccumulateGrad kernels).  Consequences, on purpose: ``torch.autograd.grad`` w.r.t. the parameters returns None for
+    them -- unless a parameter carries a hook, in which case the real per-tensor gradients are returned to autograd so
+    that hooks and AccumulateGrad behave normally (the slow path).  Parameters with ``requires_grad=False`` get no gradient.
+    """
+
     @staticmethod
-    def forward(ctx, x, owner, *params):
+    def forward(ctx, x, owner, groups, *params):
         N.require_cuda_f32(x, "input image batch")
         if x.dim() != 4 or x.shape[1] != 3:
             raise RuntimeError("expected input of shape [N,3,H,W], got %s" % (tuple(x.shape),))
         B, _, H, W = x.shape
+        if groups not in (1, 2) or B % groups:
+            raise RuntimeError("bn_groups must be 1 or 2 and divide the batch size (got %d for a batch of %d)" % (groups, B))
         D = owner.num_classes
         flat, bufs = owner._ensure_flat(x.device)
-        training = 1 if owner.training else 0
-        keep = bool(training) and any(ctx.needs_input_grad)   # grad mode is off inside Function.forward; this is the signal
+        keep = any(ctx.needs_input_grad)    # grad mode is off inside Function.forward; this is the signal
+        # train(): batch statistics.  eval(): running statistics -- folded into the convs when nothing is differentiated,
+        # kept un-folded with the activations saved when a gradient is wanted (the reference can backpropagate through an
+        # eval()-mode network: frozen BatchNorm statistics)
+        mode = N.MODE_TRAIN if owner.training else (N.MODE_EVAL_SAVE if keep else N.MODE_INFER)
         prec = owner.precision
         owner._register_weight_cache(flat, prec)
-        ws_bytes = N.lib.ddn_resnet34_8s_workspace_bytes(B, H, W, D, training, prec)
+        ws_bytes = N.lib.ddn_resnet34_8s_workspace_bytes(B, H, W, D, mode, prec)
         if ws_bytes == 0:
             raise N.DdnError("bad shape for Resnet34_8s: %s" % N.lib.ddn_last_error().decode())
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
         y = torch.empty(B, D, H, W, dtype=torch.float32, device=x.device)
         N.check(N.lib.ddn_resnet34_8s_forward(N.ptr(x), N.ptr(flat), N.ptr(bufs), N.ptr(y), N.ptr(ws), ws_bytes,
-                                              B, H, W, D, training, _BN_MOMENTUM, _BN_EPS, prec, N.stream_ptr()))
-        if training:
-            torch._foreach_add_(owner._nbt, 1)
+                                              B, H, W, D, mode, groups, _BN_MOMENTUM, _BN_EPS, prec, N.stream_ptr()))
+        if owner.training:
+            torch._foreach_add_(owner._nbt, groups)
         if keep:
-            ctx.owner, ctx.ws, ctx.shape, ctx.prec = owner, ws, (B, H, W, D), prec
+            ctx.owner, ctx.ws, ctx.shape, ctx.prec, ctx.mode, ctx.groups = owner, ws, (B, H, W, D), prec, mode, groups
             ctx.param_version = owner._flat_version
         ctx.keep = keep
         return y
@@ -72,7 +87,10 @@ class _Backbone(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         if not ctx.keep:
-            raise RuntimeError("Resnet34_8s.backward: forward ran in eval mode or without grad; nothing was saved")
+            raise RuntimeError("Resnet34_8s.backward: nothing required a gradient in the forward; no activations were saved")
+        if ctx.ws is None:
+            raise RuntimeError("Resnet34_8s: trying to backward through the backbone a second time; its saved activations "
+                               "(one caller-owned workspace) were released by the first backward -- retain_graph is not supported")
         owner = ctx.owner
         B, H, W, D = ctx.shape
         if owner._flat_version != ctx.param_version:
@@ -82,26 +100,48 @@ class _Backbone(torch.autograd.Function):
         flat, _ = owner._ensure_flat(dy.device)
         owner._register_weight_cache(flat, ctx.prec)
         grads = torch.empty_like(flat)
+        hook = owner._bucket_hook        # data_parallel.GradientAllReducer: all-reduce each bucket while the backward still runs
+        cb = N.NO_BUCKET_CALLBACK
+        if hook is not None:
+            if owner._pad_index is not None:     # the padding words travel through the all-reduce: define them
+                grads.index_fill_(0, owner._pad_index.to(grads.device), 0.0)
+            dy = dy * hook.cotangent_scale()     # the mean over ranks, folded into the (linear) backward
+
+            def _on_bucket(_user, bucket, offset, numel, _g=grads, _h=hook):
+                _h.__call_bucket__(_g, int(bucket), int(offset), int(numel))
+            cb = N.GRAD_BUCKET_FN(_on_bucket)
         N.check(N.lib.ddn_resnet34_8s_backward(N.ptr(dy), N.ptr(flat), N.ptr(grads), N.ptr(ctx.ws), ctx.ws.numel(),
-                                               B, H, W, D, _BN_EPS, ctx.prec, N.stream_ptr()))
+                                               B, H, W, D, ctx.mode, ctx.groups, _BN_EPS, ctx.prec, cb, None, N.stream_ptr()))
         ctx.ws = None
-        if owner._pad_index is not None:           # alignment padding between tensors: keep it zero (it is all-reduced / stepped too)
-            grads.index_fill_(0, owner._pad_index.to(grads.device), 0.0)
-        # Gradients are accumulated by THIS function into one flat array that every p.grad aliases (like a fused
-        # "main_grad"): the second backward of a step (image B, then image A) is one flat add instead of 110 small
-        # AccumulateGrad kernels, and the data-parallel all-reduce / a fused optimizer see a single buffer.
+        if hook is not None:
+            hook.finish(grads)
         ps = owner._params
+        if hook is None and owner._pad_index is not None:   # alignment padding between tensors: keep it zero (it is all-reduced / stepped too)
+            grads.index_fill_(0, owner._pad_index.to(grads.device), 0.0)
+        wants = ctx.needs_input_grad[3:]
+        for p, want, (_, _, o, n) in zip(ps, wants, owner._ptab):
+            if not want:
+                grads[o:o + n].zero_()      # frozen parameter: no gradient, and nothing for a flat optimizer / all-reduce to see
+        if any(p._backward_hooks or getattr(p, "_post_accumulate_grad_hooks", None) for p in ps):
+            # slow path: hand the per-tensor gradients to autograd (hooks, AccumulateGrad, autograd.grad all work)
+            return (None, None, None) + tuple(grads[o:o + n].view(s) if want else None
+                                              for want, (_, s, o, n) in zip(wants, owner._ptab))
         fg = owner._flat_grad
-        fresh = (fg is None or ps[0].grad is None or ps[-1].grad is None or fg.device != grads.device or
-                 ps[0].grad.data_ptr() != fg.data_ptr() + 4 * owner._ptab[0][2] or
-                 ps[-1].grad.data_ptr() != fg.data_ptr() + 4 * owner._ptab[-1][2])
-        if fresh:                      # first backward since zero_grad(set_to_none=True)
+        fresh = fg is None or fg.device != grads.device
+        if not fresh:
+            base = fg.data_ptr()
+            for p, want, (_, _, o, _) in zip(ps, wants, owner._ptab):
+                if want and (p.grad is None or p.grad.data_ptr() != base + 4 * o):
+                    fresh = True
+                    break
+        if fresh:                      # first backward since zero_grad(set_to_none=True) (or a partial one: start over)
             owner._flat_grad = grads
-            for p, (_, s, o, n) in zip(ps, owner._ptab):
-                p.grad = grads[o:o + n].view(s)
+            for p, want, (_, s, o, n) in zip(ps, wants, owner._ptab):
+                if want:
+                    p.grad = grads[o:o + n].view(s)
         else:
             fg.add_(grads)
-        return (None, None) + (None,) * len(ps)
+        return (None, None, None) + (None,) * len(ps)
 
 
 class Resnet34_8s(nn.Module):
@@ -125,7 +165,7 @@ class Resnet34_8s(nn.Module):
         self._pad_index = torch.tensor(pads, dtype=torch.long) if pads else None
         self._wcache = None
         self._wcache_nonce = 0
-        self._param_epoch = 0
+        self._bucket_hook = None      # data_parallel.GradientAllReducer: called per finished gradient bucket during backward
         self._params = []
         self._nbt = []
         root = _Holder()
@@ -225,8 +265,9 @@ class Resnet34_8s(nn.Module):
         return out
 
     def _register_weight_cache(self, flat, prec):
-        """Packed bf16 weights are cached across the calls of a step and re-packed when the parameters change (the
-        tensor version counter of the flat array advances on every in-place update of it or of any view)."""
+        """Gives the library a buffer for the packed bf16 weights of every conv.  Nothing here tracks parameter changes: the
+        library fingerprints the flat parameter array ON THE DEVICE at the start of every forward and re-packs when (and only
+        when) it changed, so writes through ``.data``, raw pointers, optimizers or NCCL can never leave stale packs in use."""
         if prec == N.PRECISION_FP32_SIMT:
             return
         if self._wcache is None or self._wcache.device != flat.device:
@@ -234,14 +275,11 @@ class Resnet34_8s(nn.Module):
                                        device=flat.device)
             _cache_nonce[0] += 1           # a fresh buffer may reuse the address of a dead one: never look "unchanged"
             self._wcache_nonce = _cache_nonce[0]
-        # p.data = view shares storage but NOT the autograd version counter with the flat array, so the key is the sum of the
-        # parameters' own counters (every optimizer / load_state_dict / init write advances one of them) plus manual bumps
-        version = (self._wcache_nonce << 44) + ((self._flat_version + self._param_epoch) << 32) + (sum(p._version for p in self._params) & 0xffffffff)
-        N.check(N.lib.ddn_resnet34_8s_set_weight_cache(N.ptr(self._wcache), self._wcache.numel(), N.ptr(flat), version, prec))
+        N.check(N.lib.ddn_resnet34_8s_set_weight_cache(N.ptr(self._wcache), self._wcache.numel(), N.ptr(flat),
+                                                       (self._wcache_nonce << 20) + self._flat_version, prec))
 
     def mark_parameters_changed(self):
-        """Call after writing parameters through a raw pointer / ``.data`` (anything autograd's version counters miss)."""
-        self._param_epoch += 1
+        """Kept for callers of round 1: a no-op now (parameter changes are detected on the device)."""
 
     @property
     def flat_gradient(self):
@@ -255,8 +293,10 @@ class Resnet34_8s(nn.Module):
         """The single fp32 array every parameter aliases (valid after the module is on its device)."""
         return self._ensure_flat(self._params[0].device)[0]
 
-    def forward(self, x, feature_alignment=False):
+    def forward(self, x, feature_alignment=False, bn_groups=1):
+        """``bn_groups=2``: the batch is two consecutive groups (image-A batch, image-B batch), each normalised by its own
+        batch statistics -- the two forward calls of a reference training step in one launch sequence."""
         if feature_alignment:
             raise NotImplementedError("feature_alignment=True is not on the dense-descriptor hot path "
                                       "(resnet_dilated.py:314 is never taken by the reference)")
-        return _Backbone.apply(x, self, *self._params)
+        return _Backbone.apply(x, self, bn_groups, *self._params)
