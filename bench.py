@@ -204,6 +204,13 @@ def workload_text(cfg, H, W, extra=""):
                                                             cfg["masked"], cfg["background"], extra))
 
 
+def _library_mapped():
+    try:
+        return "libddn_b200" in open("/proc/self/maps").read()
+    except Exception:
+        return None
+
+
 def run_reference_arm(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -223,6 +230,7 @@ def run_reference_arm(args, cfg):
                                    % (steps, cfg["pairs_per_gpu"], warm, wall)},
         "e2e": {"value": rate, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "libddn_b200_mapped": _library_mapped(),      # must be false: this arm is the oracle alone
     }
     print(json.dumps(line))
 
@@ -379,8 +387,20 @@ def run_ours(args, cfg):
     blind = loss_composer.empty_tensor().to(dev)
     h2d_bytes = sum(pinned[k].numel() * pinned[k].element_size() for k in keys)
 
+    side = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)] if args.two_streams else None
+
     def forward_loss_backward(d):
-        if args.two_calls:
+        if args.two_streams:      # EXPERIMENT (timing only: shared BN buffers / pack cache / flat gradient are raced)
+            cur = torch.cuda.current_stream()
+            for s_ in side:
+                s_.wait_stream(cur)
+            with torch.cuda.stream(side[0]):
+                ya = dcn.forward(d["img_a"])
+            with torch.cuda.stream(side[1]):
+                yb = dcn.forward(d["img_b"])
+            for s_ in side:
+                cur.wait_stream(s_)
+        elif args.two_calls:
             ya, yb = dcn.forward(d["img_a"]), dcn.forward(d["img_b"])
         else:
             ya, yb = dcn.forward_pair(d["img_a"], d["img_b"])
@@ -585,11 +605,12 @@ def main():
     ap.add_argument("--width", type=int, default=640)
     ap.add_argument("--matches", type=int, default=None)
     ap.add_argument("--non-matches", type=int, default=None)
-    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16x3", "bf16"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "bf16x3", "bf16"])
     ap.add_argument("--quick", "--no-cpu-baseline", dest="quick", action="store_true",
                     help="skip the forward_b16 / gpu_torch_baseline / cpu_baseline legs")
     ap.add_argument("--two-calls", action="store_true",
                     help="forward(A), forward(B) as two calls (the reference API) instead of DenseCorrespondenceNetwork.forward_pair")
+    ap.add_argument("--two-streams", action="store_true", help="experiment: the two forward calls (and their backwards) on two CUDA streams")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: all-reduce after backward instead of overlapped with it")
     ap.add_argument("--l2-pixel-loss", action="store_true",
                     help="configs[4] variant: use_l2_pixel_loss_on_masked_non_matches=True (M_pixel=50)")

@@ -147,6 +147,11 @@ typedef struct {
   int32_t flags;
   float margin;  /* M_descriptor of this term */
   float m_pixel; /* M_pixel                   */
+  /* Ragged batches (real SpartanDataset samples have a different number of matches per pair: num_matching_attempts is
+   * only an upper bound, dense_correspondence/dataset/spartan_dataset_masked.py:652-660,841-858): rows are padded to n
+   * (n_gt) with -1 and len[b] (len_gt[b]) gives pair b's true count.  DEVICE pointers [B], NULL = every pair has n (n_gt). */
+  const int64_t* len;
+  const int64_t* len_gt;
 } ddn_loss_term;
 
 #define DDN_MAX_TERMS 8
@@ -177,6 +182,8 @@ typedef struct {
   int32_t scale_by_hard_negatives;
   int32_t has_blind;
   int64_t n_match, n_masked, n_background, n_blind;
+  /* ragged batches: per-pair true counts, DEVICE pointers [B] (NULL = the n_* above for every pair) */
+  const int64_t* len_match; const int64_t* len_masked; const int64_t* len_background; const int64_t* len_blind;
 } ddn_within_scene_cfg;
 
 int ddn_within_scene_compose(const double* sums, const int64_t* counts, int B, int n_terms,
@@ -240,9 +247,13 @@ int ddn_scale_inplace(float* g, int64_t n, float scale, void* stream);
  * (element (p, c) at p*stride_p + c*stride_c, p = u + W*v) with the smallest L2 distance -- the device-side equivalent of
  * DenseCorrespondenceNetwork.find_best_match (dense_correspondence/network/dense_correspondence_network.py:488-525), first
  * minimum on ties like numpy.argmin.  best_uv [Q,2] int64 = (u, v), best_diff [Q] = that distance; norm_diffs (optional)
- * [Q, H*W] = the full distance maps.  scratch: Q x 8 bytes. */
+ * [Q, H*W] = the full distance maps.  mask_b (optional, [H*W] fp32, 1 inside / 0 outside the object mask): additionally
+ * the best match restricted to the mask, argmin(norm_diffs + (1 - mask_b) * 1e6) like
+ * dense_correspondence/evaluation/evaluation.py:1052-1059 -> best_uv_masked [Q,2], best_diff_masked [Q] (the masked
+ * minimum itself, +1e6 outside).  scratch: 2 x Q x 8 bytes. */
 int ddn_find_best_match(const float* res_b, int64_t stride_p, int64_t stride_c, int H, int W, int D,
                         const float* queries, int Q, int64_t* best_uv, float* best_diff, float* norm_diffs,
+                        const float* mask_b, int64_t* best_uv_masked, float* best_diff_masked,
                         void* scratch, void* stream);
 
 /* Non-match sampling on the device: out_b[j] = flat index (u + W*v) of a pixel drawn uniformly from the nonzero pixels of

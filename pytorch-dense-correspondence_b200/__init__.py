@@ -12,8 +12,8 @@ from .dense_correspondence_network import DenseCorrespondenceNetwork
 from .pixelwise_contrastive_loss import PixelwiseContrastiveLoss, DEFAULT_LOSS_CONFIG
 from . import loss_composer
 from .loss_composer import SpartanDatasetDataType
-from .fused_adam import FusedAdam
+from .fused_adam import FusedAdam, adjust_learning_rate
 from . import ops, synthetic, data_parallel, sampling
 
 __all__ = ["Resnet34_8s", "DenseCorrespondenceNetwork", "PixelwiseContrastiveLoss", "loss_composer",
-           "SpartanDatasetDataType", "DEFAULT_LOSS_CONFIG", "set_default_precision", "FusedAdam", "ops", "synthetic", "data_parallel", "sampling"]
+           "SpartanDatasetDataType", "DEFAULT_LOSS_CONFIG", "set_default_precision", "FusedAdam", "adjust_learning_rate", "ops", "synthetic", "data_parallel", "sampling"]

@@ -28,7 +28,8 @@ class TensorEntry(ctypes.Structure):
 
 class LossTerm(ctypes.Structure):
     _fields_ = [("idx_a", vp), ("idx_b", vp), ("gt_b", vp), ("n", i64), ("n_gt", i64),
-                ("kind", ctypes.c_int32), ("flags", ctypes.c_int32), ("margin", f32), ("m_pixel", f32)]
+                ("kind", ctypes.c_int32), ("flags", ctypes.c_int32), ("margin", f32), ("m_pixel", f32),
+                ("len", vp), ("len_gt", vp)]
 
 
 class ProfileEntry(ctypes.Structure):
@@ -38,7 +39,8 @@ class ProfileEntry(ctypes.Structure):
 class WithinSceneCfg(ctypes.Structure):
     _fields_ = [("match_loss_weight", f32), ("non_match_loss_weight", f32),
                 ("scale_by_hard_negatives", ctypes.c_int32), ("has_blind", ctypes.c_int32),
-                ("n_match", i64), ("n_masked", i64), ("n_background", i64), ("n_blind", i64)]
+                ("n_match", i64), ("n_masked", i64), ("n_background", i64), ("n_blind", i64),
+                ("len_match", vp), ("len_masked", vp), ("len_background", vp), ("len_blind", vp)]
 
 
 _SIGNATURES = {
@@ -74,7 +76,7 @@ _SIGNATURES = {
     "ddn_sample_non_matches": (i32, [vp, i32, i32, vp, vp, i64, vp, i64, vp, vp, vp, sz, vp]),
     "ddn_find_pixel_correspondences_scratch_bytes": (sz, [i64]),
     "ddn_find_pixel_correspondences": (i32, [vp, vp, i32, i32, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
-    "ddn_find_best_match": (i32, [vp, i64, i64, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp]),
+    "ddn_find_best_match": (i32, [vp, i64, i64, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "ddn_adam_step": (i32, [vp, vp, vp, vp, i64, i64, f32, f32, f32, f32, f32, f32, vp]),
     "ddn_profile_enable": (i32, [i32]),
     "ddn_profile_reset": (i32, []),

@@ -15,10 +15,11 @@ from . import _native as N
 
 class Term(object):
     """One list of index pairs scored one way (see ddn_loss_term in include/ddn_b200.h)."""
-    __slots__ = ("idx_a", "idx_b", "kind", "margin", "gt_b", "m_pixel")
+    __slots__ = ("idx_a", "idx_b", "kind", "margin", "gt_b", "m_pixel", "lengths", "gt_lengths")
 
-    def __init__(self, idx_a, idx_b, kind, margin=0.0, gt_b=None, m_pixel=0.0):
+    def __init__(self, idx_a, idx_b, kind, margin=0.0, gt_b=None, m_pixel=0.0, lengths=None, gt_lengths=None):
         self.idx_a, self.idx_b, self.kind, self.margin, self.gt_b, self.m_pixel = idx_a, idx_b, kind, margin, gt_b, m_pixel
+        self.lengths, self.gt_lengths = lengths, gt_lengths      # ragged batches: [B] int64 true counts (rows padded with -1)
 
 
 def _as_pred(pred, name):
@@ -43,6 +44,14 @@ def _as_index(idx, B, name):
     if idx.dim() != 2 or idx.shape[0] != B:
         raise RuntimeError("%s must have shape [n] or [B, n] with B=%d, got %s" % (name, B, tuple(idx.shape)))
     return idx.contiguous()
+
+
+def _as_lengths(t, B, name):
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.int64 or t.shape != (B,):
+        raise RuntimeError("%s must be a CUDA int64 tensor of shape [%d]" % (name, B))
+    return t.contiguous()
 
 
 def _strides(pa, pb):
@@ -73,6 +82,14 @@ def _build_terms(terms, B):
             arr[i].gt_b, arr[i].n_gt = gt.data_ptr(), gt.shape[1]
             arr[i].flags = N.TERM_PIXEL_WEIGHT
             arr[i].m_pixel = float(t.m_pixel)
+            gl = _as_lengths(t.gt_lengths, B, "gt_lengths of term %d" % i)
+            if gl is not None:
+                keep.append(gl)
+                arr[i].len_gt = gl.data_ptr()
+        ln = _as_lengths(t.lengths, B, "lengths of term %d" % i)
+        if ln is not None:
+            keep.append(ln)
+            arr[i].len = ln.data_ptr()
     return arr, keep
 
 
@@ -151,7 +168,7 @@ class _WithinScene(torch.autograd.Function):
 
 
 def within_scene_loss(pred_a, pred_b, image_width, terms, match_loss_weight, non_match_loss_weight,
-                      scale_by_hard_negatives, has_blind):
+                      scale_by_hard_negatives, has_blind, lengths=None):
     """terms = [match, masked, background(, blind)].  -> (loss [1], (match, masked, background, blind) [4], counts [B,T]).
     Mean over the B pairs; only ``loss`` carries gradient (the other four are logging values,
     dense_correspondence/training/training.py:369-411)."""
@@ -161,4 +178,12 @@ def within_scene_loss(pred_a, pred_b, image_width, terms, match_loss_weight, non
     n = [_as_index(t.idx_a, B, "indices").shape[1] for t in terms]
     cfg = N.WithinSceneCfg(float(match_loss_weight), float(non_match_loss_weight), int(bool(scale_by_hard_negatives)),
                            int(bool(has_blind)), n[0], n[1], n[2], n[3] if has_blind else 0)
+    keep = []
+    if lengths is not None:      # ragged batch: per-pair true counts, (matches, masked, background[, blind])
+        for field, t in zip(("len_match", "len_masked", "len_background", "len_blind"), lengths):
+            t = _as_lengths(t, B, field)
+            if t is not None:
+                keep.append(t)
+                setattr(cfg, field, t.data_ptr())
+    cfg._keep = keep
     return _WithinScene.apply(pred_a, pred_b, int(image_width), list(terms), cfg)

@@ -50,16 +50,17 @@ BnAccum bn_accum_at(void* base, int C) {
 }
 
 static inline int bn_rows_per_iter(int C) { return BN_THREADS / (C / 4); }
-// blocks per group: ~2 CTAs per SM over all groups, at least 4 row iterations per block
+// blocks per group: one resident wave over all groups (the loop keeps only a few 16-byte loads in flight per thread, so the
+// memory-level parallelism has to come from resident CTAs: 4 per SM at 59 registers), at least 4 row iterations per block
 static int bn_colsum_blocks(int64_t Mg, int C, int G) {
   const int rpi = bn_rows_per_iter(C);
-  const int64_t target = std::max<int64_t>(1, (int64_t)num_sms() * 2 / G);
+  const int64_t target = std::max<int64_t>(1, (int64_t)num_sms() * 4 / G);
   const int64_t iters = std::max<int64_t>(4, ceil_div(Mg, (int64_t)rpi * target));
   return (int)ceil_div(Mg, (int64_t)rpi * iters);
 }
 static int64_t bn_colsum_rows_per_block(int64_t Mg, int C, int G) {
   const int rpi = bn_rows_per_iter(C);
-  const int64_t target = std::max<int64_t>(1, (int64_t)num_sms() * 2 / G);
+  const int64_t target = std::max<int64_t>(1, (int64_t)num_sms() * 4 / G);
   const int64_t iters = std::max<int64_t>(4, ceil_div(Mg, (int64_t)rpi * target));
   return (int64_t)rpi * iters;
 }
@@ -189,21 +190,24 @@ bn_apply_kernel(BnApplyArgs a) {
   }
   __syncthreads();
   const int q = C >> 2;
+  const bool q_pow2 = (q & (q - 1)) == 0;
   const int64_t total = a.M * q;
   const int64_t per_group = (a.M / G) * q;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % q) << 2;
-    const float* b = sm + (G > 1 ? (int)(i / per_group) : 0) * per_g;
-    const float* sc = b; const float* mu = b + C; const float* be = b + 2 * C;
+    const int c = (q_pow2 ? (int)(i & (q - 1)) : (int)(i % q)) << 2;           // no 64-bit division on the hot path
+    const float* b = sm + ((G > 1 && i >= per_group) ? 1 : 0) * per_g;              // G <= 2
+    const float4 sc = *reinterpret_cast<const float4*>(b + c), mu = *reinterpret_cast<const float4*>(b + C + c),
+                 be = *reinterpret_cast<const float4*>(b + 2 * C + c);
     float4 v = __ldg(reinterpret_cast<const float4*>(a.x) + i);
-    v.x = fmaf(v.x - mu[c], sc[c], be[c]); v.y = fmaf(v.y - mu[c + 1], sc[c + 1], be[c + 1]);
-    v.z = fmaf(v.z - mu[c + 2], sc[c + 2], be[c + 2]); v.w = fmaf(v.w - mu[c + 3], sc[c + 3], be[c + 3]);
+    v.x = fmaf(v.x - mu.x, sc.x, be.x); v.y = fmaf(v.y - mu.y, sc.y, be.y);
+    v.z = fmaf(v.z - mu.z, sc.z, be.z); v.w = fmaf(v.w - mu.w, sc.w, be.w);
     if (a.r) {
       float4 r = __ldg(reinterpret_cast<const float4*>(a.r) + i);
       if (res_bn) {
-        const float* rsc = b + 3 * C; const float* rmu = b + 4 * C; const float* rbe = b + 5 * C;
-        r.x = fmaf(r.x - rmu[c], rsc[c], rbe[c]); r.y = fmaf(r.y - rmu[c + 1], rsc[c + 1], rbe[c + 1]);
-        r.z = fmaf(r.z - rmu[c + 2], rsc[c + 2], rbe[c + 2]); r.w = fmaf(r.w - rmu[c + 3], rsc[c + 3], rbe[c + 3]);
+        const float4 rsc = *reinterpret_cast<const float4*>(b + 3 * C + c), rmu = *reinterpret_cast<const float4*>(b + 4 * C + c),
+                     rbe = *reinterpret_cast<const float4*>(b + 5 * C + c);
+        r.x = fmaf(r.x - rmu.x, rsc.x, rbe.x); r.y = fmaf(r.y - rmu.y, rsc.y, rbe.y);
+        r.z = fmaf(r.z - rmu.z, rsc.z, rbe.z); r.w = fmaf(r.w - rmu.w, rsc.w, rbe.w);
       }
       v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
     } else if (a.r_hi) {       // identity residual from the operand planes: r = hi + lo
@@ -238,12 +242,15 @@ bn_bwd_apply_kernel(BnBwdArgs a) {
   }
   __syncthreads();
   const int q = C >> 2;
+  const bool q_pow2 = (q & (q - 1)) == 0;
   const int64_t total = a.M * q;
   const int64_t per_group = Mg * q;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % q) << 2;
-    const float* b = sm + (G > 1 ? (int)(i / per_group) : 0) * 7 * C;
-    const float* k1 = b; const float* mu = b + C; const float* is = b + 2 * C; const float* mb = b + 3 * C; const float* mg = b + 4 * C;
+    const int c = (q_pow2 ? (int)(i & (q - 1)) : (int)(i % q)) << 2;
+    const float* b = sm + ((G > 1 && i >= per_group) ? 1 : 0) * 7 * C;
+    const float4 k1 = *reinterpret_cast<const float4*>(b + c), mu = *reinterpret_cast<const float4*>(b + C + c),
+                 is = *reinterpret_cast<const float4*>(b + 2 * C + c), mb = *reinterpret_cast<const float4*>(b + 3 * C + c),
+                 mg = *reinterpret_cast<const float4*>(b + 4 * C + c);
     float4 g = __ldg(reinterpret_cast<const float4*>(a.dy) + i);
     float4 v = __ldg(reinterpret_cast<const float4*>(a.x) + i);
     if (a.relu) {
@@ -253,19 +260,19 @@ bn_bwd_apply_kernel(BnBwdArgs a) {
         float4 o = __ldg(reinterpret_cast<const float4*>(a.y) + i);
         g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
       } else if (recompute_mask) {
-        const float* sc = b + 5 * C; const float* be = b + 6 * C;
-        if (!(fmaf(v.x - mu[c], sc[c], be[c]) > 0.f)) g.x = 0.f;
-        if (!(fmaf(v.y - mu[c + 1], sc[c + 1], be[c + 1]) > 0.f)) g.y = 0.f;
-        if (!(fmaf(v.z - mu[c + 2], sc[c + 2], be[c + 2]) > 0.f)) g.z = 0.f;
-        if (!(fmaf(v.w - mu[c + 3], sc[c + 3], be[c + 3]) > 0.f)) g.w = 0.f;
+        const float4 sc = *reinterpret_cast<const float4*>(b + 5 * C + c), be = *reinterpret_cast<const float4*>(b + 6 * C + c);
+        if (!(fmaf(v.x - mu.x, sc.x, be.x) > 0.f)) g.x = 0.f;
+        if (!(fmaf(v.y - mu.y, sc.y, be.y) > 0.f)) g.y = 0.f;
+        if (!(fmaf(v.z - mu.z, sc.z, be.z) > 0.f)) g.z = 0.f;
+        if (!(fmaf(v.w - mu.w, sc.w, be.w) > 0.f)) g.w = 0.f;
       }
     }
     if (a.g_out) reinterpret_cast<float4*>(a.g_out)[i] = g;
     float4 d;
-    d.x = k1[c] * (g.x - mb[c] - (v.x - mu[c]) * is[c] * mg[c]);
-    d.y = k1[c + 1] * (g.y - mb[c + 1] - (v.y - mu[c + 1]) * is[c + 1] * mg[c + 1]);
-    d.z = k1[c + 2] * (g.z - mb[c + 2] - (v.z - mu[c + 2]) * is[c + 2] * mg[c + 2]);
-    d.w = k1[c + 3] * (g.w - mb[c + 3] - (v.w - mu[c + 3]) * is[c + 3] * mg[c + 3]);
+    d.x = k1.x * (g.x - mb.x - (v.x - mu.x) * is.x * mg.x);
+    d.y = k1.y * (g.y - mb.y - (v.y - mu.y) * is.y * mg.y);
+    d.z = k1.z * (g.z - mb.z - (v.z - mu.z) * is.z * mg.z);
+    d.w = k1.w * (g.w - mb.w - (v.w - mu.w) * is.w * mg.w);
     if (a.dx) reinterpret_cast<float4*>(a.dx)[i] = d;
     if (a.dx_hi) store_split4(a.dx_hi, a.dx_lo, i, d);
   }
@@ -367,7 +374,19 @@ static int check_c(int C, int G, int64_t M) {
   DDN_CHECK_ARG(G >= 1 && G <= BN_MAX_GROUPS && M % G == 0, "BatchNorm groups: need 1 <= G <= %d dividing the row count", BN_MAX_GROUPS);
   return 0;
 }
-static int ew_blocks(int64_t total) { return (int)std::min<int64_t>(ceil_div(total, BN_THREADS), (int64_t)num_sms() * 8); }
+// Grid of a grid-stride kernel = exactly the CTAs that are resident at once (SMs x occupancy): a larger grid runs a second,
+// partial wave at low occupancy AFTER the first one has finished its (already complete-looking) share -- with 40 registers
+// per thread only 6 CTAs of 256 threads fit an SM, and the 8-per-SM grid of round 1 cost these kernels ~1.5x.
+template <typename K>
+static int resident_blocks(K kernel, size_t smem) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BN_THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 4;
+  return per_sm * num_sms();
+}
+template <typename K>
+static int ew_blocks(K kernel, size_t smem, int64_t total) {
+  return (int)std::min<int64_t>(ceil_div(total, BN_THREADS), (int64_t)resident_blocks(kernel, smem));
+}
 
 int launch_bn_stats(const float* x, int64_t M, int C, int G, BnAccum acc, float* mean, float* invstd,
                     float* running_mean, float* running_var, float momentum, float eps, cudaStream_t st) {
@@ -404,7 +423,7 @@ int launch_bn_fold(const float* rm, const float* rv, const float* gamma, const f
 int launch_bn_apply(const BnApplyArgs& a, cudaStream_t st) {
   DDN_TRY(check_c(a.C, a.G, a.M));
   const size_t smem = (size_t)a.G * ((a.r && a.rmean) ? 6 : 3) * a.C * sizeof(float);
-  DDN_LAUNCH(bn_apply_kernel, ew_blocks(a.M * (a.C / 4)), BN_THREADS, smem, st, a);
+  DDN_LAUNCH(bn_apply_kernel, ew_blocks(bn_apply_kernel, smem, a.M * (a.C / 4)), BN_THREADS, smem, st, a);
   return 0;
 }
 
@@ -418,7 +437,7 @@ int launch_bn_backward(const BnBwdArgs& a, cudaStream_t st) {
   dim3 grid((unsigned)bn_colsum_blocks(Mg, a.C, a.G), (unsigned)a.G);
   DDN_LAUNCH(bn_colsum_kernel<1>, grid, BN_THREADS, 0, st, ca, ff, fb);
   const size_t smem = (size_t)a.G * 7 * a.C * sizeof(float);
-  DDN_LAUNCH(bn_bwd_apply_kernel, ew_blocks(a.M * (a.C / 4)), BN_THREADS, smem, st, a);
+  DDN_LAUNCH(bn_bwd_apply_kernel, ew_blocks(bn_bwd_apply_kernel, smem, a.M * (a.C / 4)), BN_THREADS, smem, st, a);
   return 0;
 }
 
@@ -427,7 +446,7 @@ int launch_stem_bn_relu_pool(const float* x, const float* mean, const float* inv
                              int N, int Hc, int Wc, int C, int G, cudaStream_t st) {
   int Hp = (Hc - 1) / 2 + 1, Wp = (Wc - 1) / 2 + 1;
   int64_t total = (int64_t)N * Hp * Wp * (C / 4);
-  DDN_LAUNCH(stem_bn_relu_pool_kernel, ew_blocks(total), 256, 0, st, x, mean, invstd, gamma, beta, y, argmax, y_hi, y_lo, N, Hc, Wc, C,
+  DDN_LAUNCH(stem_bn_relu_pool_kernel, ew_blocks(stem_bn_relu_pool_kernel, 0, total), 256, 0, st, x, mean, invstd, gamma, beta, y, argmax, y_hi, y_lo, N, Hc, Wc, C,
              Hp, Wp, N / G);
   return 0;
 }
@@ -437,7 +456,7 @@ int launch_stem_pool_relu_backward(const float* dy_pool, const uint8_t* argmax, 
                                    int N, int Hc, int Wc, int C, int G, cudaStream_t st) {
   int Hp = (Hc - 1) / 2 + 1, Wp = (Wc - 1) / 2 + 1;
   int64_t total = (int64_t)N * Hc * Wc * (C / 4);
-  DDN_LAUNCH(stem_pool_relu_bwd_kernel, ew_blocks(total), 256, 0, st, dy_pool, argmax, x, mean, invstd, gamma, beta, g,
+  DDN_LAUNCH(stem_pool_relu_bwd_kernel, ew_blocks(stem_pool_relu_bwd_kernel, 0, total), 256, 0, st, dy_pool, argmax, x, mean, invstd, gamma, beta, g,
              N, Hc, Wc, C, Hp, Wp, N / G);
   return 0;
 }

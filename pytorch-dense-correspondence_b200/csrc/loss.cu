@@ -13,8 +13,10 @@ struct DevTerm {
   const int64_t* ia;
   const int64_t* ib;
   const int64_t* gt;
+  const int64_t* len;      // per-pair true counts of a ragged batch (rows padded with -1), or null
+  const int64_t* len_gt;
   int64_t n, n_gt;
-  int64_t k;           // n / n_gt (py2 integer division, pcl.py:321)
+  int64_t k;           // n / n_gt (py2 integer division, pcl.py:321) when the batch is not ragged
   int kind, flags;
   float margin, m_pixel, inv_m_pixel;
   int block_begin;     // first blockIdx.x of this term
@@ -39,7 +41,15 @@ __device__ __forceinline__ int find_term(const DevTerms& T, int bx) {
 
 __device__ __forceinline__ float pixel_weight(const DevTerm& tm, int64_t b, int64_t j, int64_t nb, int W) {
   // l2_pixel_loss: 1/M_pixel * clamp(||uv_gt - uv||_2, max=M_pixel), uv = (n % W, n // W)   (pcl.py:321-331,349-351)
-  int64_t g = tm.gt[b * tm.n_gt + j / tm.k];
+  int64_t k = tm.k;
+  if (tm.len || tm.len_gt) {      // ragged: this pair's own non-matches-per-match
+    const int64_t ng = tm.len_gt ? tm.len_gt[b] : tm.n_gt;
+    k = ng > 0 ? (tm.len ? tm.len[b] : tm.n) / ng : 1;
+    if (k < 1) k = 1;
+  }
+  int64_t gi = j / k;
+  if (gi >= tm.n_gt) gi = tm.n_gt - 1;
+  int64_t g = tm.gt[b * tm.n_gt + gi];
   float du = (float)(g % W - nb % W);
   float dv = (float)(g / W - nb / W);
   float nrm = sqrtf(du * du + dv * dv);
@@ -62,13 +72,14 @@ loss_terms_fwd_kernel(const float* __restrict__ pa, const float* __restrict__ pb
   const int64_t* ia = tm.ia + b * tm.n;
   const int64_t* ib = tm.ib + b * tm.n;
 
+  const int64_t nvalid = tm.len ? min(tm.len[b], tm.n) : tm.n;
   float acc = 0.f;
   int cnt = 0;
   int64_t ja[LOSS_ITEMS], jb[LOSS_ITEMS];
 #pragma unroll
   for (int it = 0; it < LOSS_ITEMS; ++it) {   // all index loads first (MLP)
     int64_t j = base + it * LOSS_THREADS + threadIdx.x;
-    bool ok = j < tm.n;
+    bool ok = j < nvalid;
     ja[it] = ok ? __ldg(ia + j) : -1;
     jb[it] = ok ? __ldg(ib + j) : -1;
   }
@@ -143,12 +154,13 @@ loss_terms_bwd_kernel(const float* __restrict__ pa, const float* __restrict__ pb
   const int64_t* ib = tm.ib + b * tm.n;
   const int lane = threadIdx.x & 31;
   const bool hinge = tm.kind != DDN_TERM_MATCH;
+  const int64_t nvalid = tm.len ? min(tm.len[b], tm.n) : tm.n;
 
 #pragma unroll 1
   for (int it = 0; it < LOSS_ITEMS; ++it) {
     int64_t j = base + it * LOSS_THREADS + threadIdx.x;
     int64_t na = -1, nb = -1;
-    if (j < tm.n) { na = __ldg(ia + j); nb = __ldg(ib + j); }
+    if (j < nvalid) { na = __ldg(ia + j); nb = __ldg(ib + j); }
     bool ok = na >= 0 && nb >= 0 && na < P && nb < P;
     float g[DM];
     float s2 = 0.f;
@@ -226,7 +238,8 @@ __global__ void within_scene_compose_kernel(const double* __restrict__ sums, con
   for (int b = threadIdx.x; b < B; b += 32) {
     const double* S = sums + b * n_terms;
     const unsigned long long* H = counts + b * n_terms;
-    double match = S[0] / (double)cfg.n_match;
+    const long long n_match = cfg.len_match ? (long long)cfg.len_match[b] : (long long)cfg.n_match;
+    double match = S[0] / (double)(n_match > 1 ? n_match : 1);
     double Sm = S[1], Sb = S[2], Sx = cfg.has_blind ? S[3] : 0.0;
     double scale, tm, tb, tx;
     if (cfg.scale_by_hard_negatives) {
@@ -237,8 +250,10 @@ __global__ void within_scene_compose_kernel(const double* __restrict__ sums, con
       tb = Sb / (double)(hb > 1 ? hb : 1);
       tx = Sx / (double)(hx > 1 ? hx : 1);
     } else {
-      long long nm = cfg.n_masked > 1 ? cfg.n_masked : 1, nb = cfg.n_background > 1 ? cfg.n_background : 1;
-      long long nx = cfg.n_blind > 1 ? cfg.n_blind : 1;
+      long long nm = cfg.len_masked ? (long long)cfg.len_masked[b] : (long long)cfg.n_masked;
+      long long nb = cfg.len_background ? (long long)cfg.len_background[b] : (long long)cfg.n_background;
+      long long nx = cfg.len_blind ? (long long)cfg.len_blind[b] : (long long)cfg.n_blind;
+      nm = nm > 1 ? nm : 1; nb = nb > 1 ? nb : 1; nx = nx > 1 ? nx : 1;
       scale = (double)(nm + nb);
       tm = Sm / (double)nm; tb = Sb / (double)nb; tx = Sx / (double)nx;
     }
@@ -246,7 +261,7 @@ __global__ void within_scene_compose_kernel(const double* __restrict__ sums, con
     double loss = cfg.match_loss_weight * match + cfg.non_match_loss_weight * non_match;
     acc[0] += loss; acc[1] += match; acc[2] += tm; acc[3] += tb; acc[4] += tx;
     float* cf = coef + b * n_terms;
-    cf[0] = (float)(cfg.match_loss_weight / ((double)cfg.n_match * B));
+    cf[0] = (float)(cfg.match_loss_weight / ((double)(n_match > 1 ? n_match : 1) * B));
     cf[1] = cf[2] = (float)(cfg.non_match_loss_weight / (scale * B));
     if (n_terms > 3) cf[3] = 0.f;   // blind non-matches are reported, never optimised (loss_composer.py:136-139)
   }
@@ -277,13 +292,13 @@ static int build_terms(const ddn_loss_term* th, int n_terms, DevTerms* T) {
     DDN_CHECK_ARG(h.n >= 0 && (h.n == 0 || (h.idx_a && h.idx_b)), "term %d: null indices", i);
     DDN_CHECK_ARG(h.kind >= DDN_TERM_MATCH && h.kind <= DDN_TERM_HINGE_INV, "term %d: bad kind", i);
     DevTerm& d = T->t[i];
-    d.ia = h.idx_a; d.ib = h.idx_b; d.gt = h.gt_b; d.n = h.n; d.n_gt = h.n_gt; d.k = 1;
+    d.ia = h.idx_a; d.ib = h.idx_b; d.gt = h.gt_b; d.n = h.n; d.n_gt = h.n_gt; d.k = 1; d.len = h.len; d.len_gt = h.len_gt;
     d.kind = h.kind; d.flags = h.flags; d.margin = h.margin; d.m_pixel = h.m_pixel;
     d.inv_m_pixel = h.m_pixel != 0.f ? (float)(1.0 / (double)h.m_pixel) : 0.f;
     if (h.flags & DDN_TERM_PIXEL_WEIGHT) {
-      DDN_CHECK_ARG(h.kind != DDN_TERM_MATCH && h.gt_b && h.n_gt > 0 && h.n % h.n_gt == 0 && h.n >= h.n_gt,
+      DDN_CHECK_ARG(h.kind != DDN_TERM_MATCH && h.gt_b && h.n_gt > 0 && ((h.len || h.len_gt) || (h.n % h.n_gt == 0 && h.n >= h.n_gt)),
                     "term %d: pixel weight needs gt_b with n a positive multiple of n_gt", i);
-      d.k = h.n / h.n_gt;
+      d.k = h.n >= h.n_gt ? h.n / h.n_gt : 1;
     }
     d.block_begin = blk;
     blk += (int)ceil_div(h.n, LOSS_THREADS * LOSS_ITEMS);
@@ -414,7 +429,7 @@ extern "C" int ddn_within_scene_loss_host(const float* pred_a_host, const float*
   double* sums = (double*)t0; int64_t* counts = (int64_t*)(sums + 3 * B);
   float* five = (float*)(counts + 3 * B); float* coef = five + 8;
   ddn_within_scene_cfg cfg = {match_loss_weight, non_match_loss_weight, scale_by_hard_negatives, 0,
-                              n_match, n_masked, n_background, 0};
+                              n_match, n_masked, n_background, 0, nullptr, nullptr, nullptr, nullptr};
   rc = ddn_contrastive_terms_forward(da, db, (int64_t)D * P, 1, P, B, P, D, W, terms, 3, sums, counts, st);
   if (!rc) rc = ddn_within_scene_compose(sums, counts, B, 3, &cfg, five, coef, st);
   if (!rc) rc = (int)cudaMemcpyAsync(five_host, five, 5 * sizeof(float), cudaMemcpyDeviceToHost, st);

@@ -234,11 +234,13 @@ class DenseCorrespondenceNetwork(nn.Module):
         return best_match_uv, best_match_diff, norm_diffs
 
     @staticmethod
-    def find_best_matches_cuda(pixels_a, res_a, res_b, return_norm_diffs=False):
+    def find_best_matches_cuda(pixels_a, res_a, res_b, return_norm_diffs=False, mask_b=None):
         """Device-side, batched ``find_best_match`` (net.py:488-525): ``pixels_a`` [Q,2] (u,v) integer pixels in image A,
         ``res_a`` / ``res_b`` [H,W,D] float32 CUDA descriptor images (what ``forward_single_image_tensor`` returns, any
         strides).  -> (best_uv [Q,2] int64 CUDA, best_diff [Q] float32 CUDA[, norm_diffs [Q,H,W]]) without leaving the
-        GPU; evaluation.py:993,1047 does this 100x per pair on the host after a D2H copy."""
+        GPU; evaluation.py:993,1047 does this 100x per pair on the host after a D2H copy.  ``mask_b`` ([H,W], 1 on the
+        object): the result tuple is extended by (best_uv_masked [Q,2], best_diff_masked [Q]) = the argmin of
+        ``norm_diffs + (1 - mask_b) * 1e6`` (evaluation.py:1052-1059), from the same pass."""
         from . import _native as N
         N.require_cuda_f32(res_a, "res_a", contiguous=False); N.require_cuda_f32(res_b, "res_b", contiguous=False)
         H, W, D = res_b.shape
@@ -250,10 +252,17 @@ class DenseCorrespondenceNetwork(nn.Module):
         uv = torch.empty(Q, 2, dtype=torch.int64, device=res_b.device)
         diff = torch.empty(Q, dtype=torch.float32, device=res_b.device)
         nd = torch.empty(Q, H, W, dtype=torch.float32, device=res_b.device) if return_norm_diffs else None
-        scratch = torch.empty(Q, dtype=torch.int64, device=res_b.device)
+        scratch = torch.empty(2 * Q, dtype=torch.int64, device=res_b.device)
+        mk = uvm = diffm = None
+        if mask_b is not None:
+            mk = torch.as_tensor(mask_b).to(device=res_b.device, dtype=torch.float32).reshape(H * W).contiguous()
+            uvm = torch.empty(Q, 2, dtype=torch.int64, device=res_b.device)
+            diffm = torch.empty(Q, dtype=torch.float32, device=res_b.device)
         N.check(N.lib.ddn_find_best_match(N.ptr(res_b), res_b.stride(1), res_b.stride(2), H, W, D, N.ptr(q), Q, N.ptr(uv),
-                                          N.ptr(diff), N.ptr(nd), N.ptr(scratch), N.stream_ptr()))
-        return (uv, diff, nd) if return_norm_diffs else (uv, diff)
+                                          N.ptr(diff), N.ptr(nd), N.ptr(mk), N.ptr(uvm), N.ptr(diffm), N.ptr(scratch),
+                                          N.stream_ptr()))
+        out = (uv, diff, nd) if return_norm_diffs else (uv, diff)
+        return out + (uvm, diffm) if mask_b is not None else out
 
     @staticmethod
     def find_best_match_for_descriptor(descriptor, res):

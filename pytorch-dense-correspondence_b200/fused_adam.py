@@ -13,6 +13,16 @@ import torch
 from . import _native as N
 
 
+def adjust_learning_rate(optimizer, iteration, steps_between_learning_rate_decay=250, learning_rate_decay=0.9):
+    """DenseCorrespondenceTraining.adjust_learning_rate (dense_correspondence/training/training.py:544-558) as a free
+    function: every ``steps_between_learning_rate_decay`` iterations every param group's lr is multiplied by
+    ``learning_rate_decay`` (defaults: config/dense_correspondence/training/training.yaml:16-17).  Works on ``FusedAdam`` and on
+    any torch optimizer (anything with ``param_groups``)."""
+    if iteration % steps_between_learning_rate_decay == 0:
+        for param_group in optimizer.param_groups:
+            param_group["lr"] = param_group["lr"] * learning_rate_decay
+
+
 class FusedAdam(object):
     def __init__(self, module, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         fcn = getattr(module, "fcn", module)

@@ -36,14 +36,32 @@ def is_empty(tensor):
     return (len(tensor) == 1) and bool(tensor[0] == -1)
 
 
+def pad_index_lists(lists, device=None, pad=-1):
+    """Per-pair index lists of DIFFERENT lengths (what SpartanDataset really returns: num_matching_attempts is only an upper
+    bound on the matches found, dataset/spartan_dataset_masked.py:652-660) -> (``[B, n_max]`` int64 padded with -1, ``[B]``
+    int64 true lengths) for the ``num_valid`` argument of ``get_loss`` / ``get_within_scene_loss``."""
+    B = len(lists)
+    n_max = max(1, max(int(t.numel()) for t in lists))
+    dev = device if device is not None else lists[0].device
+    out = torch.full((B, n_max), pad, dtype=torch.int64, device=dev)
+    lens = torch.empty(B, dtype=torch.int64)
+    for i, t in enumerate(lists):
+        t = t.reshape(-1)
+        out[i, :t.numel()] = t.to(dev)
+        lens[i] = t.numel()
+    return out, lens.to(dev)
+
+
 def get_loss(pixelwise_contrastive_loss, match_type,
              image_a_pred, image_b_pred,
              matches_a, matches_b,
              masked_non_matches_a, masked_non_matches_b,
              background_non_matches_a, background_non_matches_b,
-             blind_non_matches_a, blind_non_matches_b):
+             blind_non_matches_a, blind_non_matches_b, num_valid=None):
     """loss_composer.py:7-67 -> (loss, match_loss, masked_non_match_loss, background_non_match_loss,
-    blind_non_match_loss)."""
+    blind_non_match_loss).  ``num_valid`` (batch extension, optional): dict of ``[B]`` int64 CUDA tensors with the true
+    per-pair counts of ``"matches"``, ``"masked"``, ``"background"`` (and ``"blind"``) when the ``[B, n_max]`` index tensors
+    are padded with -1 (see ``pad_index_lists``)."""
     T = SpartanDatasetDataType
     mt = torch.as_tensor(match_type)
     if mt.is_cuda:
@@ -54,7 +72,7 @@ def get_loss(pixelwise_contrastive_loss, match_type,
                                      matches_a, matches_b,
                                      masked_non_matches_a, masked_non_matches_b,
                                      background_non_matches_a, background_non_matches_b,
-                                     blind_non_matches_a, blind_non_matches_b)
+                                     blind_non_matches_a, blind_non_matches_b, num_valid=num_valid)
     if bool((mt == T.SINGLE_OBJECT_ACROSS_SCENE).all()):
         return get_same_object_across_scene_loss(pixelwise_contrastive_loss, image_a_pred, image_b_pred,
                                                  blind_non_matches_a, blind_non_matches_b)
@@ -68,7 +86,7 @@ def get_within_scene_loss(pixelwise_contrastive_loss, image_a_pred, image_b_pred
                           matches_a, matches_b,
                           masked_non_matches_a, masked_non_matches_b,
                           background_non_matches_a, background_non_matches_b,
-                          blind_non_matches_a, blind_non_matches_b):
+                          blind_non_matches_a, blind_non_matches_b, num_valid=None):
     """loss_composer.py:70-143.
 
     The ``[-1]`` sentinel for "no blind non-matches" needs no host-side test here: index -1 is skipped by
@@ -78,19 +96,21 @@ def get_within_scene_loss(pixelwise_contrastive_loss, image_a_pred, image_b_pred
     cfg = pcl._config
     gt_m = matches_b if cfg["use_l2_pixel_loss_on_masked_non_matches"] else None
     gt_b = matches_b if cfg["use_l2_pixel_loss_on_background_non_matches"] else None
+    nv = num_valid or {}
     terms = [
-        Term(matches_a, matches_b, N.TERM_MATCH),
+        Term(matches_a, matches_b, N.TERM_MATCH, lengths=nv.get("matches")),
         Term(masked_non_matches_a, masked_non_matches_b, N.TERM_HINGE, cfg["M_masked"], gt_b=gt_m,
-             m_pixel=cfg["M_pixel"]),
+             m_pixel=cfg["M_pixel"], lengths=nv.get("masked"), gt_lengths=nv.get("matches")),
         Term(background_non_matches_a, background_non_matches_b, N.TERM_HINGE, cfg["M_background"], gt_b=gt_b,
-             m_pixel=cfg["M_pixel"]),
+             m_pixel=cfg["M_pixel"], lengths=nv.get("background"), gt_lengths=nv.get("matches")),
     ]
     has_blind = blind_non_matches_a is not None
     if has_blind:
-        terms.append(Term(blind_non_matches_a, blind_non_matches_b, N.TERM_HINGE, cfg["M_masked"]))
+        terms.append(Term(blind_non_matches_a, blind_non_matches_b, N.TERM_HINGE, cfg["M_masked"], lengths=nv.get("blind")))
+    lengths = (nv.get("matches"), nv.get("masked"), nv.get("background"), nv.get("blind")) if num_valid else None
     loss, rest, counts = within_scene_loss(image_a_pred, image_b_pred, pcl.image_width, terms,
                                            cfg["match_loss_weight"], cfg["non_match_loss_weight"],
-                                           cfg["scale_by_hard_negatives"], has_blind)
+                                           cfg["scale_by_hard_negatives"], has_blind, lengths=lengths)
     if pcl.debug:
         pcl.debug_data["num_hard_negatives_device"] = counts
     return loss, rest[0:1], rest[1:2], rest[2:3], rest[3:4]

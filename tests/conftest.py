@@ -9,6 +9,9 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+os.environ.setdefault("DDN_TEST_FP32_SIMT", "1")      # the fp32 CUDA-core kernels are a test-only parity instrument
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
     # the GPU boxes advertise 128 logical CPUs to a throttled container: 128 torch threads make the CPU oracle ~50x slower

@@ -110,3 +110,16 @@ def test_fused_adam_state_dict_is_torch_adam_compatible():
     bad = {"state": {}, "param_groups": [dict(sd["param_groups"][0], params=[0, 1, 2])]}
     with pytest.raises(ValueError):
         opt.load_state_dict(bad)
+
+
+def test_adjust_learning_rate_matches_the_reference_schedule():
+    """training.py:544-558 with training.yaml's steps_between_learning_rate_decay / learning_rate_decay."""
+    net = pdc_b200.Resnet34_8s(num_classes=3)
+    opt = pdc_b200.FusedAdam(net, lr=1e-4, weight_decay=1e-4)
+    ref = torch.optim.Adam([torch.nn.Parameter(torch.zeros(1))], lr=1e-4)
+    for it in range(1, 1001):
+        pdc_b200.adjust_learning_rate(opt, it, 250, 0.9)
+        if it % 250 == 0:                                           # the reference's body, verbatim semantics
+            for g in ref.param_groups:
+                g["lr"] = g["lr"] * 0.9
+    assert abs(opt.param_groups[0]["lr"] - ref.param_groups[0]["lr"]) < 1e-18 and abs(opt.param_groups[0]["lr"] - 1e-4 * 0.9 ** 4) < 1e-12

@@ -297,6 +297,18 @@ def test_find_best_matches_cuda_vs_numpy_reference():
         if i < 3:
             np.testing.assert_allclose(nd[i].cpu().numpy(), ref_nd, rtol=1e-5, atol=1e-6)
     assert (int(uv[0, 0]), int(uv[0, 1])) == (20, 10) and float(diff[0]) == 0.0     # first of the two exact matches
+    # masked variant (evaluation.py:1052-1059): best match restricted to the object mask of image b, same pass
+    mask = torch.zeros(H, W); mask[30:90, 40:130] = 1.0
+    out = pdc_b200.DenseCorrespondenceNetwork.find_best_matches_cuda(px, res_a.to(DEV), res_b.to(DEV), mask_b=mask)
+    assert len(out) == 4 and torch.equal(out[0], uv)
+    mnp = mask.numpy()
+    for i in range(Q):
+        _, _, ref_nd = pdc_b200.DenseCorrespondenceNetwork.find_best_match((int(px[i, 0]), int(px[i, 1])), ra, rb)
+        masked = ref_nd + (1 - mnp) * 1e6
+        idx = np.unravel_index(np.argmin(masked), masked.shape)
+        got = (int(out[2][i, 1]), int(out[2][i, 0]))
+        assert got == (int(idx[0]), int(idx[1])) or abs(masked[got] - masked[idx]) < 1e-6, i
+        assert mnp[got] == 1.0 and abs(float(out[3][i]) - float(masked[idx])) < 1e-5
 
 
 @pytest.mark.parametrize("mask_kind", ["blob", "none", "empty", "full", "single"])
@@ -368,3 +380,79 @@ def test_device_reprojection_match_finder_vs_restated_reference():
     assert abs(len(ga) - len(ref_a_flat)) <= 0.002 * n and same >= 0.998 * len(ref_a_flat), (len(ga), len(ref_a_flat), same)
     if len(ga) == len(ref_a_flat) and torch.equal(ga, ref_a_flat):
         assert float((gu2.cpu() - ref_b[0]).abs().max()) < 2e-2 and float((gv2.cpu() - ref_b[1]).abs().max()) < 2e-2
+
+
+# ---------------------------------------------------------------------------------------------------- round 2
+@pytest.mark.parametrize("over", [{}, {"scale_by_hard_negatives": False},
+                                  {"use_l2_pixel_loss_on_masked_non_matches": True, "use_l2_pixel_loss_on_background_non_matches": True, "M_pixel": 9}])
+def test_ragged_batch_matches_the_reference_loop(over):
+    """Real SpartanDataset samples have a different number of matches per pair (num_matching_attempts is only an upper bound,
+    dataset/spartan_dataset_masked.py:652-660), so a batch is ragged: rows padded with -1 + per-pair counts.  The fused loss
+    must equal the mean over the pairs of the reference's per-pair loss on the un-padded lists (values, all five outputs,
+    gradients)."""
+    H, W, D, B = 24, 32, 4, 3
+    P = H * W
+    gen = torch.Generator().manual_seed(11)
+    A = 0.3 * torch.randn(B, D, H, W, generator=gen); Bt = 0.3 * torch.randn(B, D, H, W, generator=gen)
+    n_match, k_m, k_b, n_blind = [41, 7, 23], 3, 2, [5, 0, 9]
+    lists = {k: [] for k in ("matches_a", "matches_b", "masked_a", "masked_b", "background_a", "background_b", "blind_a", "blind_b")}
+    for b in range(B):
+        ma = torch.randint(0, P, (n_match[b],), generator=gen); mb = torch.randint(0, P, (n_match[b],), generator=gen)
+        lists["matches_a"].append(ma); lists["matches_b"].append(mb)
+        lists["masked_a"].append(ma.repeat_interleave(k_m)); lists["masked_b"].append(torch.randint(0, P, (n_match[b] * k_m,), generator=gen))
+        lists["background_a"].append(ma.repeat_interleave(k_b)); lists["background_b"].append(torch.randint(0, P, (n_match[b] * k_b,), generator=gen))
+        if n_blind[b]:
+            lists["blind_a"].append(torch.randint(0, P, (n_blind[b],), generator=gen)); lists["blind_b"].append(torch.randint(0, P, (n_blind[b],), generator=gen))
+        else:       # this pair has no blind non-matches: the reference's [-1] sentinel
+            lists["blind_a"].append(LO.empty_tensor()); lists["blind_b"].append(LO.empty_tensor())
+    cfg = dict(LO.DEFAULT_LOSS_CONFIG); cfg.update(over)
+    # reference: per-pair loop over the un-padded lists, mean over pairs
+    Ar = A.clone().requires_grad_(); Br = Bt.clone().requires_grad_()
+    ref = LO.TorchPixelwiseContrastiveLoss([H, W], dict(cfg))
+    par, pbr = process_network_output(Ar, B, D, H, W), process_network_output(Br, B, D, H, W)
+    outs = [LO.get_within_scene_loss(ref, par[b:b + 1], pbr[b:b + 1], *[lists[k][b] for k in
+            ("matches_a", "matches_b", "masked_a", "masked_b", "background_a", "background_b", "blind_a", "blind_b")]) for b in range(B)]
+    five_r = [sum(o[i].reshape(()) for o in outs) / B for i in range(5)]
+    five_r[0].backward()
+    # ours: padded [B, n_max] + per-pair counts
+    Ag = A.to(DEV).requires_grad_(); Bg = Bt.to(DEV).requires_grad_()
+    pag, pbg = process_network_output(Ag, B, D, H, W), process_network_output(Bg, B, D, H, W)
+    pad = {k: loss_composer.pad_index_lists(v, device=DEV) for k, v in lists.items()}
+    blind_len = torch.tensor([n if n else 0 for n in n_blind], dtype=torch.int64, device=DEV)
+    nv = {"matches": pad["matches_a"][1], "masked": pad["masked_a"][1], "background": pad["background_a"][1], "blind": blind_len}
+    ours = pdc_b200.PixelwiseContrastiveLoss([H, W], dict(cfg))
+    five = loss_composer.get_loss(ours, torch.zeros(B, dtype=torch.int64), pag, pbg, pad["matches_a"][0], pad["matches_b"][0],
+                                  pad["masked_a"][0], pad["masked_b"][0], pad["background_a"][0], pad["background_b"][0],
+                                  pad["blind_a"][0], pad["blind_b"][0], num_valid=nv)
+    for i in range(5):
+        assert abs(float(five[i]) - float(five_r[i])) <= 2e-6 * max(1.0, abs(float(five_r[i]))), (i, float(five[i]), float(five_r[i]))
+    five[0].backward()
+    assert rel(Ag.grad, Ar.grad) < 1e-5 and rel(Bg.grad, Br.grad) < 1e-5
+
+
+def test_triplet_loss_matches_the_oracle():
+    """PixelwiseContrastiveLoss.get_triplet_loss / loss_composer.get_within_scene_loss_triplet
+    (pixelwise_contrastive_loss.py:103-129, loss_composer.py:145-166): values and gradients."""
+    H, W, D = 24, 32, 5
+    P = H * W
+    gen = torch.Generator().manual_seed(4)
+    A = 0.3 * torch.randn(1, D, H, W, generator=gen); Bt = 0.3 * torch.randn(1, D, H, W, generator=gen)
+    ma = torch.randint(0, P, (29,), generator=gen); mb = torch.randint(0, P, (29,), generator=gen)
+    na = ma.repeat_interleave(4); nb = torch.randint(0, P, (116,), generator=gen)
+    ga = ma.repeat_interleave(2); gb = torch.randint(0, P, (58,), generator=gen)
+    cfg = dict(LO.DEFAULT_LOSS_CONFIG)
+    ref = LO.TorchPixelwiseContrastiveLoss([H, W], cfg); ours = pdc_b200.PixelwiseContrastiveLoss([H, W], cfg)
+    Ar = A.clone().requires_grad_(); Br = Bt.clone().requires_grad_()
+    Ag = A.to(DEV).requires_grad_(); Bg = Bt.to(DEV).requires_grad_()
+    par, pbr = process_network_output(Ar, 1, D, H, W), process_network_output(Br, 1, D, H, W)
+    pag, pbg = process_network_output(Ag, 1, D, H, W), process_network_output(Bg, 1, D, H, W)
+    c = lambda t: t.to(DEV)
+    r = ref.get_triplet_loss(par, pbr, ma, mb, na, nb, 0.1)
+    o = ours.get_triplet_loss(pag, pbg, c(ma), c(mb), c(na), c(nb), 0.1)
+    assert abs(float(r) - float(o)) <= 1e-6 * max(1.0, abs(float(r)))
+    r5 = (ref.get_triplet_loss(par, pbr, ma, mb, na, nb, cfg["alpha_triplet"]) + ref.get_triplet_loss(par, pbr, ma, mb, ga, gb, cfg["alpha_triplet"]))
+    o5 = loss_composer.get_within_scene_loss_triplet(ours, pag, pbg, c(ma), c(mb), c(na), c(nb), c(ga), c(gb), None, None)
+    assert abs(float(r5) - float(o5[0])) <= 1e-6 * max(1.0, abs(float(r5)))
+    assert all(float(t) == 0.0 for t in o5[1:])
+    r5.backward(); o5[0].backward()
+    assert rel(Ag.grad, Ar.grad) < 1e-5 and rel(Bg.grad, Br.grad) < 1e-5

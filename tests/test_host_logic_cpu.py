@@ -76,6 +76,48 @@ def _worker(rank, world, port, flat_mode, q):
     dist.destroy_process_group()
 
 
+def _overlap_worker(rank, world, port, q):
+    """Host logic of the overlapped reducer: buckets all-reduced as the (here simulated) backward reports them."""
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    from pdc_b200 import data_parallel as DP
+    DP.init_from_env(backend="gloo")
+
+    class FakeBackbone(object):
+        _bucket_hook = None
+    mod = FakeBackbone()
+    params = [torch.nn.Parameter(torch.zeros(4))]
+    red = DP.GradientAllReducer(params, module=mod, overlap=True)
+    ok = mod._bucket_hook is red and abs(red.cotangent_scale() - 0.5) < 1e-12
+    flat = torch.arange(40, dtype=torch.float32) * (rank + 1) * red.cotangent_scale()     # the backward pre-scales by 1/world
+    for b, (off, n) in enumerate([(24, 16), (8, 16), (4, 4), (0, 4)]):                   # completion order: last layers first
+        red.__call_bucket__(flat, b, off, n)
+    red.finish(flat)
+    ok = ok and torch.allclose(flat, torch.arange(40, dtype=torch.float32) * 1.5) and red.overlapped_steps == 1
+    ok = ok and red.bytes_last == 40 * 4
+    red()                                              # explicit call afterwards: nothing left to do, must not reduce twice
+    ok = ok and torch.allclose(flat, torch.arange(40, dtype=torch.float32) * 1.5)
+    red.detach()
+    ok = ok and mod._bucket_hook is None
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_overlapped_allreduce_host_logic_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_overlap_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(res) == [(0, True), (1, True)]
+
+
 @pytest.mark.parametrize("flat_mode", [True, False])
 def test_gradient_allreduce_gloo_world2(flat_mode):
     ctx = mp.get_context("spawn")
@@ -100,7 +142,8 @@ def test_bench_reference_arm_prints_one_contract_line():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ)
     env.pop("RANK", None); env.pop("WORLD_SIZE", None)
-    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+    small = ["--height", "96", "--width", "128", "--pairs-per-gpu", "2", "--matches", "50", "--non-matches", "100"]   # CPU-suite sized
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"] + small,
                        capture_output=True, text=True, timeout=900, cwd=root, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
@@ -111,6 +154,7 @@ def test_bench_reference_arm_prints_one_contract_line():
         assert k in d, k
     assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["libddn_b200_mapped"] is False            # the reference arm times the oracle alone: the product library is not even loaded
     env["RANK"] = "1"; env["WORLD_SIZE"] = "2"
     r1 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
                         capture_output=True, text=True, timeout=300, cwd=root, env=env)
