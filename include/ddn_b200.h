@@ -98,11 +98,15 @@ size_t ddn_resnet34_8s_workspace_bytes(int B, int H, int W, int D, int mode, int
 int ddn_resnet34_8s_forward(const float* x, const float* params, float* buffers, float* y,
                             void* workspace, size_t workspace_bytes,
                             int B, int H, int W, int D,
-                            int mode, int bn_groups, float momentum, float eps, int precision, void* stream);
+                            int mode, int bn_groups, float momentum, float eps, int precision,
+                            float* low_nhwc_out /* optional [B, H/8*W/8, D]: the low-resolution descriptor map y is upsampled from */,
+                            void* stream);
 
 typedef void (*ddn_grad_bucket_fn)(void* user, int bucket, int64_t offset, int64_t numel);
 
-int ddn_resnet34_8s_backward(const float* dy, const float* params, float* grads,
+/* dy [B,D,H,W] and / or dlow_nhwc [B, H/8*W/8, D] (the cotangent of low_nhwc_out, produced by the loss kernels that are fused
+ * with the upsample): either may be NULL, not both. */
+int ddn_resnet34_8s_backward(const float* dy, const float* dlow_nhwc, const float* params, float* grads,
                              void* workspace, size_t workspace_bytes,
                              int B, int H, int W, int D, int mode, int bn_groups, float eps, int precision,
                              ddn_grad_bucket_fn on_bucket, void* user, void* stream);
@@ -171,6 +175,20 @@ int ddn_contrastive_terms_backward(const float* pred_a, const float* pred_b,
                                    const ddn_loss_term* terms_host, int n_terms,
                                    const float* coef, const float* upstream /* device scalar or NULL */,
                                    float* dpred_a, float* dpred_b, void* stream);
+
+/* The same two entry points FUSED WITH THE BILINEAR UPSAMPLE that produced the descriptor images
+ * (nn.functional.upsample_bilinear, resnet_dilated.py:320): low_a / low_b [B, h*w, D] are the low-resolution maps
+ * (`low_nhwc_out` of ddn_resnet34_8s_forward), index tensors still address the H x W image.  Each descriptor is blended from
+ * its 4 low-resolution cells (identical fp32 arithmetic to ddn_upsample_bilinear_forward), so sums / counts equal those of
+ * the entry points above on the upsampled image; the backward scatters into d(low) [B, h*w, D] (caller zero-fills), which
+ * ddn_resnet34_8s_backward takes as `dlow_nhwc` -- the full-resolution image and its gradient are never touched. */
+int ddn_contrastive_terms_forward_lowres(const float* low_a, const float* low_b, int B, int h, int w, int H, int W, int D,
+                                         const ddn_loss_term* terms_host, int n_terms,
+                                         double* sums, int64_t* counts, void* stream);
+int ddn_contrastive_terms_backward_lowres(const float* low_a, const float* low_b, int B, int h, int w, int H, int W, int D,
+                                          const ddn_loss_term* terms_host, int n_terms,
+                                          const float* coef, const float* upstream,
+                                          float* dlow_a, float* dlow_b, void* stream);
 
 /* loss_composer.get_within_scene_loss (dense_correspondence/loss_functions/loss_composer.py:70-143)
  * evaluated on the device from the sums/counts of terms ordered {match, masked, background[, blind]}:

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libddn_b200.so")
-SOURCES = ["engine.cu", "loss.cu", "conv_simt.cu", "bn.cu", "head.cu", "conv_tc.cu", "optim.cu", "match.cu", "sampling.cu"]
+SOURCES = ["engine.cu", "loss.cu", "loss_lowres.cu", "conv_simt.cu", "bn.cu", "head.cu", "conv_tc.cu", "optim.cu", "match.cu", "sampling.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "-cudart", "static"]

@@ -167,8 +167,49 @@ class _WithinScene(torch.autograd.Function):
         return da, db, None, None, None
 
 
+class _WithinSceneLowres(torch.autograd.Function):
+    """within_scene_loss fused with the bilinear upsample: the descriptors are blended from the low-resolution maps
+    ``low_a`` / ``low_b`` [B, h*w, D] (csrc/loss_lowres.cu); the gradient is scattered into d(low) -- the full-resolution
+    descriptor images and their gradients are never read or written."""
+
+    @staticmethod
+    def forward(ctx, low_a, low_b, geom, terms, cfg):
+        B, _, D = low_a.shape
+        h, w, H, W = geom
+        T = len(terms)
+        arr, keep = _build_terms(terms, B)
+        dev = low_a.device
+        sums = torch.empty(B, T, dtype=torch.float64, device=dev)
+        counts = torch.empty(B, T, dtype=torch.int64, device=dev)
+        five = torch.empty(5, dtype=torch.float32, device=dev)
+        coef = torch.empty(B, T, dtype=torch.float32, device=dev)
+        st = N.stream_ptr()
+        N.check(N.lib.ddn_contrastive_terms_forward_lowres(N.ptr(low_a), N.ptr(low_b), B, h, w, H, W, D, arr, T,
+                                                           N.ptr(sums), N.ptr(counts), st))
+        N.check(N.lib.ddn_within_scene_compose(N.ptr(sums), N.ptr(counts), B, T, ctypes.byref(cfg), N.ptr(five),
+                                               N.ptr(coef), st))
+        ctx.save_for_backward(low_a, low_b, coef)
+        ctx.arr, ctx.keep, ctx.geom = arr, keep, geom
+        loss = five[0:1]
+        rest = five[1:].clone()
+        ctx.mark_non_differentiable(rest, counts)
+        return loss, rest, counts
+
+    @staticmethod
+    def backward(ctx, dloss, _drest, _dcounts):
+        low_a, low_b, coef = ctx.saved_tensors
+        B, _, D = low_a.shape
+        h, w, H, W = ctx.geom
+        da = torch.zeros_like(low_a)
+        db = torch.zeros_like(low_b)
+        up = dloss.to(torch.float32).contiguous()
+        N.check(N.lib.ddn_contrastive_terms_backward_lowres(N.ptr(low_a), N.ptr(low_b), B, h, w, H, W, D, ctx.arr, len(ctx.arr),
+                                                            N.ptr(coef), N.ptr(up), N.ptr(da), N.ptr(db), N.stream_ptr()))
+        return da, db, None, None, None
+
+
 def within_scene_loss(pred_a, pred_b, image_width, terms, match_loss_weight, non_match_loss_weight,
-                      scale_by_hard_negatives, has_blind, lengths=None):
+                      scale_by_hard_negatives, has_blind, lengths=None, lowres=None):
     """terms = [match, masked, background(, blind)].  -> (loss [1], (match, masked, background, blind) [4], counts [B,T]).
     Mean over the B pairs; only ``loss`` carries gradient (the other four are logging values,
     dense_correspondence/training/training.py:369-411)."""
@@ -186,4 +227,7 @@ def within_scene_loss(pred_a, pred_b, image_width, terms, match_loss_weight, non
                 keep.append(t)
                 setattr(cfg, field, t.data_ptr())
     cfg._keep = keep
+    if lowres is not None:        # (low_a, low_b, (h, w, H, W)): both images are bilinear upsamples of these maps
+        low_a, low_b, geom = lowres
+        return _WithinSceneLowres.apply(low_a.contiguous(), low_b.contiguous(), geom, list(terms), cfg)
     return _WithinScene.apply(pred_a, pred_b, int(image_width), list(terms), cfg)

@@ -50,19 +50,16 @@ BnAccum bn_accum_at(void* base, int C) {
 }
 
 static inline int bn_rows_per_iter(int C) { return BN_THREADS / (C / 4); }
-// blocks per group: one resident wave over all groups (the loop keeps only a few 16-byte loads in flight per thread, so the
-// memory-level parallelism has to come from resident CTAs: 4 per SM at 59 registers), at least 4 row iterations per block
-static int bn_colsum_blocks(int64_t Mg, int C, int G) {
+// blocks per group: exactly one resident wave over all groups (`resident` = SMs x CTAs per SM of the kernel, from the occupancy
+// API: a larger grid would run a partial second wave at low occupancy), at least 4 row iterations per block
+static int64_t bn_colsum_rows_per_block(int64_t Mg, int C, int G, int resident) {
   const int rpi = bn_rows_per_iter(C);
-  const int64_t target = std::max<int64_t>(1, (int64_t)num_sms() * 4 / G);
-  const int64_t iters = std::max<int64_t>(4, ceil_div(Mg, (int64_t)rpi * target));
-  return (int)ceil_div(Mg, (int64_t)rpi * iters);
-}
-static int64_t bn_colsum_rows_per_block(int64_t Mg, int C, int G) {
-  const int rpi = bn_rows_per_iter(C);
-  const int64_t target = std::max<int64_t>(1, (int64_t)num_sms() * 4 / G);
+  const int64_t target = std::max<int64_t>(1, (int64_t)resident / G);
   const int64_t iters = std::max<int64_t>(4, ceil_div(Mg, (int64_t)rpi * target));
   return (int64_t)rpi * iters;
+}
+static int bn_colsum_blocks(int64_t Mg, int C, int G, int resident) {
+  return (int)ceil_div(Mg, bn_colsum_rows_per_block(Mg, C, G, resident));
 }
 
 struct BnColsumArgs {
@@ -93,19 +90,18 @@ bn_colsum_kernel(BnColsumArgs a, BnFwdFinal ff, BnBwdFinal fb) {
       sc = make_float4(ga.x * is.x, ga.y * is.y, ga.z * is.z, ga.w * is.w);
     }
   }
-  for (int64_t r = r0 + rr; r < r1; r += rpi) {
-    float4 v = __ldg(reinterpret_cast<const float4*>(a.x + r * C) + cq);
+  // two rows per iteration: twice the loads in flight per thread (the kernel is pure streaming; its speed is the number of
+  // outstanding 16-byte loads per SM)
+  auto accumulate = [&](const float4 v, float4 gr, const uint2 yh, const float4 yo) {
     if (MODE == 0) {
       s0.x += v.x; s0.y += v.y; s0.z += v.z; s0.w += v.w;
       s1.x = fmaf(v.x, v.x, s1.x); s1.y = fmaf(v.y, v.y, s1.y); s1.z = fmaf(v.z, v.z, s1.z); s1.w = fmaf(v.w, v.w, s1.w);
     } else {
-      float4 gr = __ldg(reinterpret_cast<const float4*>(a.dy + r * C) + cq);
       if (a.relu) {
         if (a.y_hi) {     // the bf16 "hi" plane of y has y's sign and zero-ness
-          mask_from_bf16x4(__ldg(reinterpret_cast<const uint2*>(a.y_hi + r * C) + cq), gr);
+          mask_from_bf16x4(yh, gr);
         } else if (a.y) {
-          float4 o = __ldg(reinterpret_cast<const float4*>(a.y + r * C) + cq);
-          gr.x = o.x > 0.f ? gr.x : 0.f; gr.y = o.y > 0.f ? gr.y : 0.f; gr.z = o.z > 0.f ? gr.z : 0.f; gr.w = o.w > 0.f ? gr.w : 0.f;
+          gr.x = yo.x > 0.f ? gr.x : 0.f; gr.y = yo.y > 0.f ? gr.y : 0.f; gr.z = yo.z > 0.f ? gr.z : 0.f; gr.w = yo.w > 0.f ? gr.w : 0.f;
         } else {          // no residual in the forward: y > 0  <=>  bn(x) > 0, same fmaf as bn_apply_kernel
           if (!(fmaf(v.x - mu.x, sc.x, be.x) > 0.f)) gr.x = 0.f;
           if (!(fmaf(v.y - mu.y, sc.y, be.y) > 0.f)) gr.y = 0.f;
@@ -117,6 +113,31 @@ bn_colsum_kernel(BnColsumArgs a, BnFwdFinal ff, BnBwdFinal fb) {
       s1.x = fmaf(gr.x, (v.x - mu.x) * is.x, s1.x); s1.y = fmaf(gr.y, (v.y - mu.y) * is.y, s1.y);
       s1.z = fmaf(gr.z, (v.z - mu.z) * is.z, s1.z); s1.w = fmaf(gr.w, (v.w - mu.w) * is.w, s1.w);
     }
+  };
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const uint2 z2 = make_uint2(0u, 0u);
+  int64_t r = r0 + rr;
+  for (; r + rpi < r1; r += 2 * rpi) {
+    const int64_t ra = r, rb = r + rpi;
+    const float4 va = __ldg(reinterpret_cast<const float4*>(a.x + ra * C) + cq), vb = __ldg(reinterpret_cast<const float4*>(a.x + rb * C) + cq);
+    float4 ga = z4, gb = z4, ya = z4, yb = z4; uint2 ha = z2, hb = z2;
+    if (MODE == 1) {
+      ga = __ldg(reinterpret_cast<const float4*>(a.dy + ra * C) + cq); gb = __ldg(reinterpret_cast<const float4*>(a.dy + rb * C) + cq);
+      if (a.relu && a.y_hi) { ha = __ldg(reinterpret_cast<const uint2*>(a.y_hi + ra * C) + cq); hb = __ldg(reinterpret_cast<const uint2*>(a.y_hi + rb * C) + cq); }
+      else if (a.relu && a.y) { ya = __ldg(reinterpret_cast<const float4*>(a.y + ra * C) + cq); yb = __ldg(reinterpret_cast<const float4*>(a.y + rb * C) + cq); }
+    }
+    accumulate(va, ga, ha, ya);
+    accumulate(vb, gb, hb, yb);
+  }
+  for (; r < r1; r += rpi) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(a.x + r * C) + cq);
+    float4 gr = z4, yo = z4; uint2 yh = z2;
+    if (MODE == 1) {
+      gr = __ldg(reinterpret_cast<const float4*>(a.dy + r * C) + cq);
+      if (a.relu && a.y_hi) yh = __ldg(reinterpret_cast<const uint2*>(a.y_hi + r * C) + cq);
+      else if (a.relu && a.y) yo = __ldg(reinterpret_cast<const float4*>(a.y + r * C) + cq);
+    }
+    accumulate(v, gr, yh, yo);
   }
   __shared__ float4 sh0[BN_THREADS], sh1[BN_THREADS];
   __shared__ int s_last;
@@ -392,10 +413,11 @@ int launch_bn_stats(const float* x, int64_t M, int C, int G, BnAccum acc, float*
                     float* running_mean, float* running_var, float momentum, float eps, cudaStream_t st) {
   DDN_TRY(check_c(C, G, M));
   const int64_t Mg = M / G;
-  BnColsumArgs a = {x, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, Mg, C, bn_colsum_rows_per_block(Mg, C, G), 0};
+  const int resident = resident_blocks(bn_colsum_kernel<0>, 0);
+  BnColsumArgs a = {x, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, Mg, C, bn_colsum_rows_per_block(Mg, C, G, resident), 0};
   BnFwdFinal ff = {acc, mean, invstd, running_mean, running_var, Mg, G, C, momentum, eps};
   BnBwdFinal fb = {};
-  dim3 grid((unsigned)bn_colsum_blocks(Mg, C, G), (unsigned)G);
+  dim3 grid((unsigned)bn_colsum_blocks(Mg, C, G, resident), (unsigned)G);
   DDN_LAUNCH(bn_colsum_kernel<0>, grid, BN_THREADS, 0, st, a, ff, fb);
   return 0;
 }
@@ -430,11 +452,12 @@ int launch_bn_apply(const BnApplyArgs& a, cudaStream_t st) {
 int launch_bn_backward(const BnBwdArgs& a, cudaStream_t st) {
   DDN_TRY(check_c(a.C, a.G, a.M));
   const int64_t Mg = a.M / a.G;
-  BnColsumArgs ca = {a.x, a.dy, a.y, a.y_hi, a.mean, a.invstd, a.gamma, a.beta, Mg, a.C, bn_colsum_rows_per_block(Mg, a.C, a.G), a.relu};
+  const int resident = resident_blocks(bn_colsum_kernel<1>, 0);
+  BnColsumArgs ca = {a.x, a.dy, a.y, a.y_hi, a.mean, a.invstd, a.gamma, a.beta, Mg, a.C, bn_colsum_rows_per_block(Mg, a.C, a.G, resident), a.relu};
   DDN_CHECK_ARG(!(a.relu && !a.y && !a.y_hi) || a.beta, "recomputing the ReLU mask needs beta");
   BnFwdFinal ff = {};
   BnBwdFinal fb = {a.acc, a.sums, a.dgamma, a.dbeta, a.G, a.C};
-  dim3 grid((unsigned)bn_colsum_blocks(Mg, a.C, a.G), (unsigned)a.G);
+  dim3 grid((unsigned)bn_colsum_blocks(Mg, a.C, a.G, resident), (unsigned)a.G);
   DDN_LAUNCH(bn_colsum_kernel<1>, grid, BN_THREADS, 0, st, ca, ff, fb);
   const size_t smem = (size_t)a.G * 7 * a.C * sizeof(float);
   DDN_LAUNCH(bn_bwd_apply_kernel, ew_blocks(bn_bwd_apply_kernel, smem, a.M * (a.C / 4)), BN_THREADS, smem, st, a);

@@ -73,8 +73,10 @@ int launch_stem_pool_relu_backward(const float* dy_pool, const uint8_t* argmax, 
 // head.cu
 int launch_nchw_to_nhwc4(const float* x, float* y, int N, int H, int W, cudaStream_t st);
 // feat [N*Mimg][C]: fp32 (`feat`) or bf16 planes (feat = hi + lo) when feat == nullptr
+// low [N, D, Mimg] (NCHW, read by the upsample) and optionally low_nhwc [N, Mimg, D] (read by the fused loss)
 int launch_fc_forward(const float* feat, const __nv_bfloat16* feat_hi, const __nv_bfloat16* feat_lo, const float* w, const float* bias,
-                      float* low, int64_t Mimg, int N, int C, int D, cudaStream_t st);
+                      float* low, float* low_nhwc, int64_t Mimg, int N, int C, int D, cudaStream_t st);
+int launch_add_lowres_nhwc(const float* dlow_nhwc, float* dlow, int64_t Mimg, int N, int D, int accumulate, cudaStream_t st);
 int launch_fc_backward(const float* dlow, const float* feat, const __nv_bfloat16* feat_hi, const __nv_bfloat16* feat_lo, const float* w,
                        float* dfeat, float* dw, float* dbias, int64_t Mimg, int N, int C, int D, cudaStream_t st);
 int launch_upsample_fwd(const float* x, float* y, int NC, int h, int w, int H, int W, cudaStream_t st);

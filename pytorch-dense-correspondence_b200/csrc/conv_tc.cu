@@ -830,43 +830,47 @@ constexpr int STEM_COLS = 2 * STEM_TW + 5;
 __global__ void __launch_bounds__(256)
 stem_patch_split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                         int N, int H, int W, int H1, int W1, int want_lo) {
-  __shared__ float tile[3][7][STEM_COLS + 1];
+  __shared__ float tile[3 * 7 * (STEM_COLS + 1) + 4];
+  __shared__ int koff[192];          // k -> offset of (c, r, s) inside `tile` (the + 2*px part is added per pixel); -1 = zero padding
   const int wt = blockIdx.x, ho = blockIdx.y, n = blockIdx.z;
   const int wo0 = wt * STEM_TW;
   const int h_base = 2 * ho - 3, w_base = 2 * wo0 - 3;
+  for (int k = threadIdx.x; k < 192; k += blockDim.x) {
+    int off = -1;
+    if (k < 147) { const int c = k % 3, rs = k / 3, r = rs / 7, sx = rs - r * 7; off = (c * 7 + r) * (STEM_COLS + 1) + sx; }
+    koff[k] = off;
+  }
   for (int i = threadIdx.x; i < 3 * 7 * STEM_COLS; i += blockDim.x) {
     int col = i % STEM_COLS, rc = i / STEM_COLS;
     int r = rc % 7, c = rc / 7;
     int h = h_base + r, w = w_base + col;
     float v = 0.f;
     if (h >= 0 && h < H && w >= 0 && w < W) v = __ldg(x + (((int64_t)n * 3 + c) * H + h) * W + w);
-    tile[c][r][col] = v;
+    tile[(c * 7 + r) * (STEM_COLS + 1) + col] = v;
   }
   __syncthreads();
   const int npix = min(STEM_TW, W1 - wo0);
-  for (int i = threadIdx.x; i < npix * 48; i += blockDim.x) {
-    const int kq = i % 48, px = i / 48;
-    float v[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int k = kq * 4 + j;
-      float val = 0.f;
-      if (k < 147) {
-        const int c = k % 3, rs = k / 3, r = rs / 7, sx = rs - r * 7;
-        val = tile[c][r][2 * px + sx];
+  // thread -> a fixed group of 4 consecutive k (its four tile offsets live in registers), looping over the pixels
+  const int kq = threadIdx.x % 48, px0 = threadIdx.x / 48;
+  const int pstep = blockDim.x / 48;            // 256 threads: 5 pixels per sweep (16 threads idle)
+  if (px0 < pstep) {
+    const int o0 = koff[kq * 4], o1 = koff[kq * 4 + 1], o2 = koff[kq * 4 + 2], o3 = koff[kq * 4 + 3];
+    for (int px = px0; px < npix; px += pstep) {
+      const int b2 = 2 * px;
+      float v[4];
+      v[0] = o0 >= 0 ? tile[o0 + b2] : 0.f; v[1] = o1 >= 0 ? tile[o1 + b2] : 0.f;
+      v[2] = o2 >= 0 ? tile[o2 + b2] : 0.f; v[3] = o3 >= 0 ? tile[o3 + b2] : 0.f;
+      const int64_t o = (((int64_t)n * H1 + ho) * W1 + wo0 + px) * 48 + kq;
+      __nv_bfloat16 h0 = __float2bfloat16_rn(v[0]), h1 = __float2bfloat16_rn(v[1]), h2 = __float2bfloat16_rn(v[2]), h3 = __float2bfloat16_rn(v[3]);
+      __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
+      uint2 hv; hv.x = *reinterpret_cast<uint32_t*>(&a); hv.y = *reinterpret_cast<uint32_t*>(&b);
+      reinterpret_cast<uint2*>(hi)[o] = hv;
+      if (want_lo) {
+        __nv_bfloat162 c2 = __halves2bfloat162(__float2bfloat16_rn(v[0] - __bfloat162float(h0)), __float2bfloat16_rn(v[1] - __bfloat162float(h1)));
+        __nv_bfloat162 d2 = __halves2bfloat162(__float2bfloat16_rn(v[2] - __bfloat162float(h2)), __float2bfloat16_rn(v[3] - __bfloat162float(h3)));
+        uint2 lv; lv.x = *reinterpret_cast<uint32_t*>(&c2); lv.y = *reinterpret_cast<uint32_t*>(&d2);
+        reinterpret_cast<uint2*>(lo)[o] = lv;
       }
-      v[j] = val;
-    }
-    const int64_t o = (((int64_t)n * H1 + ho) * W1 + wo0 + px) * 48 + kq;
-    __nv_bfloat16 h0 = __float2bfloat16_rn(v[0]), h1 = __float2bfloat16_rn(v[1]), h2 = __float2bfloat16_rn(v[2]), h3 = __float2bfloat16_rn(v[3]);
-    __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
-    uint2 hv; hv.x = *reinterpret_cast<uint32_t*>(&a); hv.y = *reinterpret_cast<uint32_t*>(&b);
-    reinterpret_cast<uint2*>(hi)[o] = hv;
-    if (want_lo) {
-      __nv_bfloat162 c2 = __halves2bfloat162(__float2bfloat16_rn(v[0] - __bfloat162float(h0)), __float2bfloat16_rn(v[1] - __bfloat162float(h1)));
-      __nv_bfloat162 d2 = __halves2bfloat162(__float2bfloat16_rn(v[2] - __bfloat162float(h2)), __float2bfloat16_rn(v[3] - __bfloat162float(h3)));
-      uint2 lv; lv.x = *reinterpret_cast<uint32_t*>(&c2); lv.y = *reinterpret_cast<uint32_t*>(&d2);
-      reinterpret_cast<uint2*>(lo)[o] = lv;
     }
   }
 }

@@ -390,7 +390,7 @@ static int fill_eval_stats(const Ctx& c) {
   return launch_bn_eval_stats_all(c.buffers, reinterpret_cast<float*>(c.ws), segs.data(), (int)segs.size(), c.G, c.eps, c.st);
 }
 
-static int net_forward(const Ctx& c, const float* x, float* y) {
+static int net_forward(const Ctx& c, const float* x, float* y, float* low_nhwc) {
   const NetSpec& s = *c.s; const Plan& p = *c.p;
   const int B = p.B, G = c.G;
   const bool want_lo = p.precision == DDN_PRECISION_BF16X3;
@@ -469,7 +469,7 @@ static int net_forward(const Ctx& c, const float* x, float* y) {
   const bool feat_planes = p.tc;       // the features are read from the operand planes (hi + lo)
   DDN_TRY(launch_fc_forward(feat_planes ? nullptr : cur, feat_planes ? c.h(cur_p.hi) : nullptr,
                             (feat_planes && want_lo) ? c.h(cur_p.lo) : nullptr, c.params + s.fc_w, c.params + s.fc_b, c.f(p.low),
-                            (int64_t)h8 * w8, B, 512, p.D, c.st));
+                            low_nhwc, (int64_t)h8 * w8, B, 512, p.D, c.st));
   DDN_TRY(launch_upsample_fwd(c.f(p.low), y, B * p.D, h8, w8, p.H, p.W, c.st));
   return 0;
 }
@@ -541,7 +541,7 @@ static int bn_backward_for(const Ctx& c, const BnSpec& bs, const ConvBufs& cb, c
 // gradient buckets, in the order the backward completes them (ddn_grad_bucket_fn): [first block of the layer .. next bucket)
 struct Bucket { int64_t begin, end; };
 
-static int net_backward(const Ctx& c, const float* dy, ddn_grad_bucket_fn on_bucket, void* user) {
+static int net_backward(const Ctx& c, const float* dy, const float* dlow_nhwc, ddn_grad_bucket_fn on_bucket, void* user) {
   const NetSpec& s = *c.s; const Plan& p = *c.p;
   const int B = p.B, h8 = p.H / 8, w8 = p.W / 8;
   const bool want_lo = p.precision == DDN_PRECISION_BF16X3;
@@ -549,7 +549,9 @@ static int net_backward(const Ctx& c, const float* dy, ddn_grad_bucket_fn on_buc
   DDN_CUDA(cudaMemsetAsync(c.ws + p.acc, 0, bn_accum_bytes(512), c.st));
   if (p.tc) DDN_CUDA(cudaMemsetAsync(c.f(p.dwp_all), 0, sizeof(float) * (size_t)(s.n_params + 64 * 192), c.st));
   const BlockBufs& last = p.blk.back();
-  DDN_TRY(launch_upsample_bwd(dy, c.f(p.dlow), B * p.D, h8, w8, p.H, p.W, c.st));
+  // d(low) = upsample^T(dy) [+ the gradient the fused loss scattered straight into the low-resolution map]
+  if (dy) DDN_TRY(launch_upsample_bwd(dy, c.f(p.dlow), B * p.D, h8, w8, p.H, p.W, c.st));
+  if (dlow_nhwc) DDN_TRY(launch_add_lowres_nhwc(dlow_nhwc, c.f(p.dlow), (int64_t)h8 * w8, B, p.D, dy ? 1 : 0, c.st));
   int cur = 0;   // index of the scratch buffer holding d(block output)
   DDN_TRY(launch_fc_backward(c.f(p.dlow), p.tc ? nullptr : c.f(last.out), p.tc ? c.h(last.out_p.hi) : nullptr,
                              (p.tc && want_lo) ? c.h(last.out_p.lo) : nullptr, c.params + s.fc_w, S[cur], c.grads + s.fc_w,
@@ -726,28 +728,29 @@ static int check_groups(int B, int G) {
 
 extern "C" int ddn_resnet34_8s_forward(const float* x, const float* params, float* buffers, float* y,
                                        void* workspace, size_t workspace_bytes, int B, int H, int W, int D,
-                                       int mode, int bn_groups, float momentum, float eps, int precision, void* stream) {
+                                       int mode, int bn_groups, float momentum, float eps, int precision, float* low_nhwc_out,
+                                       void* stream) {
   DDN_CHECK_ARG(x && params && buffers && y, "null tensor");
   DDN_TRY(check_groups(B, bn_groups));
   Plan p;
   DDN_TRY(make_plan(&p, B, H, W, D, mode, precision));
   DDN_TRY(check_ws(p, workspace, workspace_bytes));
   Ctx c = {&get_spec(D), &p, (char*)workspace, params, buffers, nullptr, (cudaStream_t)stream, momentum, eps, mode, bn_groups};
-  return net_forward(c, x, y);
+  return net_forward(c, x, y, low_nhwc_out);
 }
 
-extern "C" int ddn_resnet34_8s_backward(const float* dy, const float* params, float* grads,
+extern "C" int ddn_resnet34_8s_backward(const float* dy, const float* dlow_nhwc, const float* params, float* grads,
                                         void* workspace, size_t workspace_bytes, int B, int H, int W, int D,
                                         int mode, int bn_groups, float eps, int precision,
                                         ddn_grad_bucket_fn on_bucket, void* user, void* stream) {
-  DDN_CHECK_ARG(dy && params && grads, "null tensor");
+  DDN_CHECK_ARG((dy || dlow_nhwc) && params && grads, "null tensor");
   DDN_CHECK_ARG(mode == DDN_MODE_TRAIN || mode == DDN_MODE_EVAL_SAVE, "backward needs a forward that kept its activations (mode %d)", mode);
   DDN_TRY(check_groups(B, bn_groups));
   Plan p;
   DDN_TRY(make_plan(&p, B, H, W, D, mode, precision));
   DDN_TRY(check_ws(p, workspace, workspace_bytes));
   Ctx c = {&get_spec(D), &p, (char*)workspace, params, nullptr, grads, (cudaStream_t)stream, 0.f, eps, mode, bn_groups};
-  return net_backward(c, dy, on_bucket, user);
+  return net_backward(c, dy, dlow_nhwc, on_bucket, user);
 }
 
 extern "C" int ddn_resnet34_8s_grad_buckets(int D, int64_t* offsets, int cap) {

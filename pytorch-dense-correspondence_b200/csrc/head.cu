@@ -37,7 +37,7 @@ template <int DM>
 __global__ void __launch_bounds__(256)
 fc_forward_kernel(const float* __restrict__ feat, const __nv_bfloat16* __restrict__ feat_hi, const __nv_bfloat16* __restrict__ feat_lo,
                   const float* __restrict__ w, const float* __restrict__ bias,
-                  float* __restrict__ low, int64_t Mimg, int N, int C, int D) {
+                  float* __restrict__ low, float* __restrict__ low_t, int64_t Mimg, int N, int C, int D) {
   extern __shared__ float ws[];   // [D][C]
   for (int i = threadIdx.x; i < D * C; i += blockDim.x) ws[i] = w[i];
   __syncthreads();
@@ -63,7 +63,10 @@ fc_forward_kernel(const float* __restrict__ feat, const __nv_bfloat16* __restric
     for (int d = 0; d < DM; ++d) {
       if (d < D) {
         float s = warp_sum(acc[d]);
-        if (lane == 0) low[(n * D + d) * Mimg + p] = s + bias[d];
+        if (lane == 0) {
+          low[(n * D + d) * Mimg + p] = s + bias[d];
+          if (low_t) low_t[pix * D + d] = s + bias[d];       // NHWC copy for the loss fused with the upsample (loss_lowres.cu)
+        }
       }
     }
   }
@@ -237,14 +240,14 @@ int launch_nchw_to_nhwc4(const float* x, float* y, int N, int H, int W, cudaStre
   } while (0)
 
 int launch_fc_forward(const float* feat, const __nv_bfloat16* feat_hi, const __nv_bfloat16* feat_lo, const float* w, const float* bias,
-                      float* low, int64_t Mimg, int N, int C, int D, cudaStream_t st) {
+                      float* low, float* low_nhwc, int64_t Mimg, int N, int C, int D, cudaStream_t st) {
   DDN_CHECK_ARG(feat || feat_hi, "fc: no feature tensor");
   DDN_CHECK_ARG(D >= 1 && D <= FC_MAXD && C % 4 == 0 && C <= 512, "fc: need 1<=D<=32, C%%4==0, C<=512");
   size_t smem = sizeof(float) * D * C;
   int blocks = (int)std::min<int64_t>(ceil_div((int64_t)N * Mimg, 8), (int64_t)num_sms() * 8);
 #define CALL(DM)                                                                                              \
   DDN_CUDA(cudaFuncSetAttribute(fc_forward_kernel<DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-  DDN_LAUNCH(fc_forward_kernel<DM>, blocks, 256, smem, st, feat, feat_hi, feat_lo, w, bias, low, Mimg, N, C, D)
+  DDN_LAUNCH(fc_forward_kernel<DM>, blocks, 256, smem, st, feat, feat_hi, feat_lo, w, bias, low, low_nhwc, Mimg, N, C, D)
   FC_DISPATCH(D, CALL);
 #undef CALL
   return 0;
@@ -285,6 +288,22 @@ int launch_upsample_bwd(const float* dy, float* dx, int NC, int h, int w, int H,
   float ish = sh > 0 ? 1.f / sh : (float)H, isw = sw > 0 ? 1.f / sw : (float)W;
   int64_t total = (int64_t)NC * h * w;
   DDN_LAUNCH(upsample_bwd_kernel, (int)ceil_div(total, 128), 128, 0, st, dy, dx, NC, h, w, H, W, sh, sw, ish, isw);
+  return 0;
+}
+
+// dlow [N, D, Mimg] (+)= dlow_t [N, Mimg, D]: the gradient the fused loss scattered into the NHWC low-resolution map
+__global__ void add_lowres_nhwc_kernel(const float* __restrict__ dlow_t, float* __restrict__ dlow, int64_t Mimg, int N, int D, int accumulate) {
+  const int64_t total = (int64_t)N * D * Mimg;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i % Mimg; const int64_t t = i / Mimg;
+    const int d = (int)(t % D); const int64_t n = t / D;
+    const float v = __ldg(dlow_t + (n * Mimg + p) * D + d);
+    dlow[i] = accumulate ? dlow[i] + v : v;
+  }
+}
+int launch_add_lowres_nhwc(const float* dlow_t, float* dlow, int64_t Mimg, int N, int D, int accumulate, cudaStream_t st) {
+  const int64_t total = (int64_t)N * D * Mimg;
+  DDN_LAUNCH(add_lowres_nhwc_kernel, ew_blocks(total, 256), 256, 0, st, dlow_t, dlow, Mimg, N, D, accumulate);
   return 0;
 }
 

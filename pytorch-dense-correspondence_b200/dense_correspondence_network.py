@@ -116,6 +116,10 @@ class DenseCorrespondenceNetwork(nn.Module):
         B = img_a.shape[0]
         res = self.fcn(torch.cat([img_a, img_b], 0), bn_groups=2)
         res_a, res_b = res[:B], res[B:]
+        tag = resnet_dilated.lowres_of(res)
+        if tag is not None:
+            resnet_dilated.attach_lowres(res_a, tag[0][:B], tag[1], tag[2])
+            resnet_dilated.attach_lowres(res_b, tag[0][B:], tag[1], tag[2])
         if self._normalize:
             res_a = res_a / torch.norm(res_a, 2, 1)
             res_b = res_b / torch.norm(res_b, 2, 1)
@@ -139,8 +143,11 @@ class DenseCorrespondenceNetwork(nn.Module):
         """[N,D,H,W] -> strided view [N, W*H, D] (net.py:303-319)."""
         W = self._image_width
         H = self._image_height
+        tag = resnet_dilated.lowres_of(image_pred)
         image_pred = image_pred.view(N, self.descriptor_dimension, W * H)
         image_pred = image_pred.permute(0, 2, 1)
+        if tag is not None:       # a view of the same storage (shares the version counter): the tag stays valid
+            resnet_dilated.attach_lowres(image_pred, tag[0], tag[1], tag[2])
         return image_pred
 
     def clip_pixel_to_image_size_and_round(self, uv):

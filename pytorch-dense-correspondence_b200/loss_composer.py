@@ -10,10 +10,28 @@ Batch extension (the reference is batch-1 only, training.py:314-323): descriptor
 ``[B, W*H, D]`` with ``[B, n]`` index tensors; the loss is then the mean over the B pairs of the reference's
 per-pair loss.
 """
+import os
+
 import torch
 
 from . import _native as N
 from .contrastive_ops import Term, within_scene_loss, contrastive_terms
+from .resnet_dilated import lowres_of
+
+
+def _fused_lowres(image_a_pred, image_b_pred, image_width):
+    """When both descriptor images are untouched outputs of Resnet34_8s (they carry the low-resolution map they were upsampled
+    from), the loss is evaluated THROUGH the upsample: (low_a, low_b, (h, w, H, W)), else None.  DDN_FUSED_UPSAMPLE_LOSS=0
+    forces the generic gather from the full-resolution images (A/B measurements, tests)."""
+    if os.environ.get("DDN_FUSED_UPSAMPLE_LOSS", "1") == "0":
+        return None
+    ta, tb = lowres_of(image_a_pred), lowres_of(image_b_pred)
+    if ta is None or tb is None or ta[1:3] != tb[1:3] or ta[2] != image_width or ta[0].shape != tb[0].shape:
+        return None
+    H, W = ta[1], ta[2]
+    if ta[0].dim() != 3 or ta[0].shape[1] != (H // 8) * (W // 8) or image_a_pred.shape[-2] != H * W:
+        return None
+    return ta[0], tb[0], (H // 8, W // 8, H, W)
 
 
 class SpartanDatasetDataType:
@@ -110,7 +128,8 @@ def get_within_scene_loss(pixelwise_contrastive_loss, image_a_pred, image_b_pred
     lengths = (nv.get("matches"), nv.get("masked"), nv.get("background"), nv.get("blind")) if num_valid else None
     loss, rest, counts = within_scene_loss(image_a_pred, image_b_pred, pcl.image_width, terms,
                                            cfg["match_loss_weight"], cfg["non_match_loss_weight"],
-                                           cfg["scale_by_hard_negatives"], has_blind, lengths=lengths)
+                                           cfg["scale_by_hard_negatives"], has_blind, lengths=lengths,
+                                           lowres=_fused_lowres(image_a_pred, image_b_pred, pcl.image_width))
     if pcl.debug:
         pcl.debug_data["num_hard_negatives_device"] = counts
     return loss, rest[0:1], rest[1:2], rest[2:3], rest[3:4]

@@ -44,6 +44,21 @@ def _check_precision(prec):
                            "(set DDN_TEST_FP32_SIMT=1 to use them); the product path is precision 'bf16x3' on the tensor cores")
 
 
+def attach_lowres(y, low, H, W):
+    """Tags a descriptor image with the low-resolution map it is the bilinear upsample of.  loss_composer looks for the tag and,
+    when both images of a pair carry it, evaluates the loss through the 4 low-resolution cells of every sampled pixel
+    (csrc/loss_lowres.cu) instead of gathering from the full-resolution tensor.  The tag records the tensor's version so that an
+    in-place modification of the image silently falls back to the generic path."""
+    y._ddn_lowres = (low, int(H), int(W), y._version)
+
+
+def lowres_of(t):
+    tag = getattr(t, "_ddn_lowres", None)
+    if tag is None or t._version != tag[3]:
+        return None
+    return tag
+
+
 class _Holder(nn.Module):
     """A name-space node of the reference module tree (it owns parameters/buffers, never computes)."""
 
@@ -85,18 +100,24 @@ class _Backbone(torch.autograd.Function):
             raise N.DdnError("bad shape for Resnet34_8s: %s" % N.lib.ddn_last_error().decode())
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
         y = torch.empty(B, D, H, W, dtype=torch.float32, device=x.device)
+        # the low-resolution map y is the bilinear upsample of, [B, H/8*W/8, D]: second output, so that a loss fused with the
+        # upsample (contrastive_ops.within_scene_loss on tensors carrying `_ddn_lowres`) can differentiate through it directly
+        low = torch.empty(B, (H // 8) * (W // 8), D, dtype=torch.float32, device=x.device)
         N.check(N.lib.ddn_resnet34_8s_forward(N.ptr(x), N.ptr(flat), N.ptr(bufs), N.ptr(y), N.ptr(ws), ws_bytes,
-                                              B, H, W, D, mode, groups, _BN_MOMENTUM, _BN_EPS, prec, N.stream_ptr()))
+                                              B, H, W, D, mode, groups, _BN_MOMENTUM, _BN_EPS, prec, N.ptr(low), N.stream_ptr()))
+        ctx.set_materialize_grads(False)
         if owner.training:
             torch._foreach_add_(owner._nbt, groups)
         if keep:
             ctx.owner, ctx.ws, ctx.shape, ctx.prec, ctx.mode, ctx.groups = owner, ws, (B, H, W, D), prec, mode, groups
             ctx.param_version = owner._flat_version
         ctx.keep = keep
-        return y
+        return y, low
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, dlow):
+        if dy is None and dlow is None:
+            return (None, None, None) + (None,) * len(ctx.owner._params) if ctx.keep else None
         if not ctx.keep:
             raise RuntimeError("Resnet34_8s.backward: nothing required a gradient in the forward; no activations were saved")
         if ctx.ws is None:
@@ -106,9 +127,14 @@ class _Backbone(torch.autograd.Function):
         B, H, W, D = ctx.shape
         if owner._flat_version != ctx.param_version:
             raise RuntimeError("parameters were re-allocated between forward and backward")
-        dy = dy.contiguous()
-        N.require_cuda_f32(dy, "descriptor cotangent")
-        flat, _ = owner._ensure_flat(dy.device)
+        ref = dy if dy is not None else dlow
+        if dy is not None:
+            dy = dy.contiguous()
+            N.require_cuda_f32(dy, "descriptor cotangent")
+        if dlow is not None:
+            dlow = dlow.contiguous()
+            N.require_cuda_f32(dlow, "low-resolution descriptor cotangent")
+        flat, _ = owner._ensure_flat(ref.device)
         owner._register_weight_cache(flat, ctx.prec)
         grads = torch.empty_like(flat)
         hook = owner._bucket_hook        # data_parallel.GradientAllReducer: all-reduce each bucket while the backward still runs
@@ -116,12 +142,14 @@ class _Backbone(torch.autograd.Function):
         if hook is not None:
             if owner._pad_index is not None:     # the padding words travel through the all-reduce: define them
                 grads.index_fill_(0, owner._pad_index.to(grads.device), 0.0)
-            dy = dy * hook.cotangent_scale()     # the mean over ranks, folded into the (linear) backward
+            sc = hook.cotangent_scale()          # the mean over ranks, folded into the (linear) backward
+            dy = dy * sc if dy is not None else None
+            dlow = dlow * sc if dlow is not None else None
 
             def _on_bucket(_user, bucket, offset, numel, _g=grads, _h=hook):
                 _h.__call_bucket__(_g, int(bucket), int(offset), int(numel))
             cb = N.GRAD_BUCKET_FN(_on_bucket)
-        N.check(N.lib.ddn_resnet34_8s_backward(N.ptr(dy), N.ptr(flat), N.ptr(grads), N.ptr(ctx.ws), ctx.ws.numel(),
+        N.check(N.lib.ddn_resnet34_8s_backward(N.ptr(dy), N.ptr(dlow), N.ptr(flat), N.ptr(grads), N.ptr(ctx.ws), ctx.ws.numel(),
                                                B, H, W, D, ctx.mode, ctx.groups, _BN_EPS, ctx.prec, cb, None, N.stream_ptr()))
         ctx.ws = None
         if hook is not None:
@@ -310,4 +338,6 @@ class Resnet34_8s(nn.Module):
         if feature_alignment:
             raise NotImplementedError("feature_alignment=True is not on the dense-descriptor hot path "
                                       "(resnet_dilated.py:314 is never taken by the reference)")
-        return _Backbone.apply(x, self, bn_groups, *self._params)
+        y, low = _Backbone.apply(x, self, bn_groups, *self._params)
+        attach_lowres(y, low, x.shape[2], x.shape[3])
+        return y

@@ -12,8 +12,11 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "pytorch-dense-correspondence_b200", "libddn_b200.so")
-PAT = re.compile(r"\b(UTCHMMA|UTMALDG(?:\.\dD)?|LDTM(?:\.x\d+)?|UTCBAR|UTCATOMSWS|SYNCS(?:\.[A-Z0-9]+)*|REDG\.E\.ADD\.F32x4|HMMA|FFMA)\b")
-KEYS = ["UTCHMMA", "UTMALDG", "LDTM", "UTCBAR", "UTCATOMSWS", "SYNCS", "REDG.E.ADD.F32x4", "HMMA", "FFMA"]
+PAT = re.compile(r"\b(UTCHMMA\.2CTA|UTCHMMA|UTMALDG\.\dD\.2CTA|UTMALDG(?:\.\dD)?|LDTM(?:\.x\d+)?|UTCBAR\.2CTA\.MULTICAST|UTCBAR|UTCATOMSWS|"
+                 r"SYNCS(?:\.[A-Z0-9]+)*|REDG\.E\.ADD\.F32x4|REDG\.E\.ADD\.F64|HMMA|FFMA)\b")
+# longest prefixes first: the .2CTA forms are the cta_group::2 (CTA-pair) variants
+KEYS = ["UTCHMMA.2CTA", "UTCHMMA", "UTMALDG.4D.2CTA", "UTMALDG.2D.2CTA", "UTMALDG", "LDTM", "UTCBAR.2CTA.MULTICAST", "UTCBAR", "UTCATOMSWS",
+        "SYNCS", "REDG.E.ADD.F32x4", "REDG.E.ADD.F64", "HMMA", "FFMA"]
 
 
 def main(tag):
@@ -38,11 +41,13 @@ def main(tag):
     out = os.path.join(ROOT, "profiles", tag + "_sass_evidence.md")
     with open(out, "w") as f:
         f.write("# %s: Blackwell SASS mnemonics per kernel of libddn_b200.so (`cuobjdump -sass`, sm_100a)\n\n" % tag)
-        f.write("UTCHMMA = `tcgen05.mma`; UTMALDG = TMA tensor load; LDTM = `tcgen05.ld`; UTCBAR = `tcgen05.commit`; UTCATOMSWS = TMEM\n"
-                "alloc/dealloc; SYNCS = mbarrier; REDG.E.ADD.F32x4 = `red.global.add.v4.f32`; HMMA = legacy `mma.sync` (none expected).\n"
+        f.write("UTCHMMA = `tcgen05.mma` (.2CTA = `cta_group::2`, the CTA-pair form); UTMALDG = TMA tensor load (.2CTA = pair form signalling the\n"
+                "leader's mbarrier); LDTM = `tcgen05.ld`; UTCBAR = `tcgen05.commit` (.2CTA.MULTICAST = to both CTAs of the pair); UTCATOMSWS = TMEM\n"
+                "alloc/dealloc; SYNCS = mbarrier; REDG.E.ADD.F32x4 = `red.global.add.v4.f32`; REDG.E.ADD.F64 = the BatchNorm-statistics reds;\n"
+                "HMMA = legacy `mma.sync` (none expected).\n"
                 "Static instruction counts (loops are not unrolled into them), kernels without any tensor/TMA instruction listed last.\n\n")
         f.write("| kernel | " + " | ".join(KEYS) + " |\n|---|" + "---:|" * len(KEYS) + "\n")
-        rows = sorted(counts.items(), key=lambda kv: (-kv[1]["UTCHMMA"], -kv[1]["FFMA"]))
+        rows = sorted(counts.items(), key=lambda kv: (-kv[1]["UTCHMMA.2CTA"], -kv[1]["UTCHMMA"], -kv[1]["FFMA"]))
         for fn, c in rows:
             name = re.sub(r"\(.*", "", demangled.get(fn, fn)).replace("void ", "")
             f.write("| `%s` | " % name[:80] + " | ".join(str(c[k]) if c[k] else "" for k in KEYS) + " |\n")

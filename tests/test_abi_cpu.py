@@ -67,7 +67,7 @@ def test_workspace_and_argument_checks():
     assert b"multiple" in N.lib.ddn_last_error() or b"dimension" in N.lib.ddn_last_error()
     # null pointers / bad sizes are refused with DDN_EINVAL and never reach a kernel launch
     before = N.launch_count()
-    assert N.lib.ddn_resnet34_8s_forward(None, None, None, None, None, 0, 1, 480, 640, 3, 1, 1, 0.1, 1e-5, 0, None) == -1
+    assert N.lib.ddn_resnet34_8s_forward(None, None, None, None, None, 0, 1, 480, 640, 3, 1, 1, 0.1, 1e-5, 0, None, None) == -1
     assert N.lib.ddn_contrastive_terms_forward(None, None, 0, 0, 0, 1, 10, 3, 4, None, 0, None, None, None) == -1
     assert N.lib.ddn_upsample_bilinear_forward(None, None, 1, 1, 1, 1, 1, None) == -1
     assert N.lib.ddn_conv2d_workspace_bytes(1, 60, 80, 64, 64, 3, 1, 1, 1, 0) >= 3 * 9 * 64 * 64 * 4

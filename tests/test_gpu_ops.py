@@ -456,3 +456,54 @@ def test_triplet_loss_matches_the_oracle():
     assert all(float(t) == 0.0 for t in o5[1:])
     r5.backward(); o5[0].backward()
     assert rel(Ag.grad, Ar.grad) < 1e-5 and rel(Bg.grad, Br.grad) < 1e-5
+
+
+@pytest.mark.parametrize("D,over", [(3, {}), (16, {}), (8, {"use_l2_pixel_loss_on_masked_non_matches": True, "M_pixel": 9,
+                                                        "scale_by_hard_negatives": False})])
+def test_loss_fused_with_the_upsample_equals_the_generic_loss(D, over):
+    """csrc/loss_lowres.cu: the loss evaluated through the bilinear upsample (4 low-resolution cells per sampled pixel) must equal
+    the loss gathered from the upsampled image -- all five outputs, hard-negative counts -- and its gradient w.r.t. the
+    low-resolution map must equal upsample^T of the generic path's full-resolution gradient."""
+    B, H, W = 2, 64, 96
+    h, w, P = H // 8, W // 8, H * W
+    gen = torch.Generator().manual_seed(21)
+    low = [(0.3 * torch.randn(B, h * w, D, generator=gen)).to(DEV) for _ in range(2)]
+    nchw = lambda t: t.view(B, h, w, D).permute(0, 3, 1, 2).contiguous()
+    ma = torch.randint(0, P, (B, 40), generator=gen).to(DEV); mb = torch.randint(0, P, (B, 40), generator=gen).to(DEV)
+    ma[:, 0] = 0; mb[:, 0] = P - 1; ma[:, 1] = W - 1; mb[:, 1] = P - W         # image corners: the clamped edge cells of the blend
+    na = ma.repeat_interleave(3, dim=1); nb = torch.randint(0, P, (B, 120), generator=gen).to(DEV)
+    ga = ma.repeat_interleave(2, dim=1); gb = torch.randint(0, P, (B, 80), generator=gen).to(DEV)
+    xa = torch.randint(0, P, (B, 17), generator=gen).to(DEV); xb = torch.randint(0, P, (B, 17), generator=gen).to(DEV)
+    cfg = dict(LO.DEFAULT_LOSS_CONFIG); cfg.update(over)
+    pcl = pdc_b200.PixelwiseContrastiveLoss([H, W], cfg)
+    pcl.debug = True
+    mt = torch.zeros(B, dtype=torch.int64)
+    from pdc_b200 import resnet_dilated
+    res = {}
+    for path in ("generic", "fused"):
+        lows = [t.clone().requires_grad_() for t in low]
+        imgs = [ops.upsample_bilinear_forward(nchw(t.detach()), H, W).requires_grad_() for t in lows]
+        preds = [y.view(B, D, P).permute(0, 2, 1) for y in imgs]
+        if path == "fused":
+            for p_, l_ in zip(preds, lows):
+                resnet_dilated.attach_lowres(p_, l_, H, W)
+        five = loss_composer.get_loss(pcl, mt, preds[0], preds[1], ma, mb, na, nb, ga, gb, xa, xb)
+        five[0].backward()
+        if path == "generic":      # push the full-resolution gradient through the upsample's adjoint
+            g = [ops.upsample_bilinear_backward(y.grad, h, w).permute(0, 2, 3, 1).reshape(B, h * w, D) for y in imgs]
+            assert lows[0].grad is None
+        else:
+            g = [t.grad for t in lows]
+            assert imgs[0].grad is None                     # the full-resolution image was never differentiated
+        res[path] = ([float(t) for t in five], pcl.debug_data["num_hard_negatives_device"].clone(), g)
+    (f0, c0, g0), (f1, c1, g1) = res["generic"], res["fused"]
+    assert torch.equal(c0, c1)
+    for a, b in zip(f0, f1):
+        assert abs(a - b) <= 2e-6 * max(1.0, abs(a)), (f0, f1)
+    assert rel(g1[0], g0[0]) < 2e-5 and rel(g1[1], g0[1]) < 2e-5
+    # a modified image must NOT use the stale low-resolution map
+    y = ops.upsample_bilinear_forward(nchw(low[0]), H, W)
+    resnet_dilated.attach_lowres(y, low[0], H, W)
+    assert resnet_dilated.lowres_of(y) is not None
+    y.mul_(2.0)
+    assert resnet_dilated.lowres_of(y) is None
