@@ -432,27 +432,33 @@ def run_ours(args, cfg):
         step(resident)
     barrier()
 
-    # ---- timed region 1: inputs resident in HBM
-    N.lib.ddn_profile_reset()
-    N.lib.ddn_profile_enable(1)
-    launches0 = N.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clk:
+    # ---- timed region 1: inputs resident in HBM.  Nothing but the step's own launches is on the stream: the per-kernel event
+    # pairs of the roofline pass below would sit between dependent kernels (one event record after every convolution, ~220
+    # per step) and defeat the programmatic dependent launch that overlaps one kernel's prologue with its predecessor's tail.
+    def timed_steps(instrumented):
+        N.lib.ddn_profile_reset()
+        N.lib.ddn_profile_enable(1 if instrumented else 0)
+        n0 = N.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
-        ev0.record()
+        e0.record()
         for _ in range(args.steps):
-            loss = step(resident)
-        ev1.record()
+            out = step(resident)
+        e1.record()
         barrier()
-    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
-    launches = N.launch_count() - launches0
-    N.lib.ddn_profile_enable(0)
-    prof = N.profile_read()
+        N.lib.ddn_profile_enable(0)
+        return max_over_ranks(e0.elapsed_time(e1)), N.launch_count() - n0, out
 
-    if args.profile_run:
+    with ClockSampler(local_rank) as clk:
+        ms_total, launches, loss = timed_steps(False)
+    # ---- timed region 1b: the same K steps again with a CUDA-event pair around every convolution / loss kernel on the launching
+    # stream (ddn_profile_*): the per-class kernel durations the roofline block is computed from
+    if args.profile_run:      # under ncu: warm-up + the timed steps only, so the launch list is exactly `steps` steps
         if rank == 0:
-            emit({"profile_run": True, "ms_per_step_under_profiler": ms_total / args.steps, "classes": prof})
+            emit({"profile_run": True, "ms_per_step_under_profiler": ms_total / args.steps})
         return
+    ms_instrumented, _, _ = timed_steps(True)
+    prof = N.profile_read()
 
     # ---- timed region 2: end to end from pinned host memory, loss read back every step.  Every step's inputs are copied
     # host->device inside the timed region (through DevicePrefetcher: the copy of step i+1 overlaps the compute of step i,
@@ -535,7 +541,10 @@ def run_ours(args, cfg):
                 "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a long step)",
                 "launches": prof[dom]["launches"], "avg_launch_ms": prof[dom]["ms"] / max(1, prof[dom]["launches"]),
                 "all_conv_achieved": (conv_fl / (conv_ms * 1e-3) / 1e12) if conv_ms > 0 else 0.0,
-                "conv_share_of_step": conv_ms / (ms_total / 1.0) if ms_total > 0 else None,
+                "conv_share_of_step": conv_ms / ms_instrumented if ms_instrumented > 0 else None,
+                "timed": "a second pass of the same %d steps with a CUDA-event pair around every convolution / loss launch on the launching "
+                         "stream; that pass took %.3f ms/step (the uninstrumented pass that `value` comes from: %.3f ms/step)"
+                         % (args.steps, ms_instrumented / args.steps, ms_total / args.steps),
                 "whole_step_achieved": value * flops_per_pair(D, H, W) / world / 1e12,
                 "arithmetic": {"fp32": "fp32 FFMA (CUDA cores)", "bf16x3": "bf16x3 split: 3 tensor-core MMAs per useful MAC",
                                "bf16": "single bf16 MMA"}[prec_name],

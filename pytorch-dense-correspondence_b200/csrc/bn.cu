@@ -73,6 +73,7 @@ struct BnColsumArgs {
 template <int MODE>
 __global__ void __launch_bounds__(BN_THREADS)
 bn_colsum_kernel(BnColsumArgs a, BnFwdFinal ff, BnBwdFinal fb) {
+  pdl_prologue();
   const int C = a.C, q = C >> 2;
   const int cq = threadIdx.x % q, rr = threadIdx.x / q, rpi = BN_THREADS / q;
   const int g = blockIdx.y;
@@ -168,6 +169,7 @@ bn_colsum_kernel(BnColsumArgs a, BnFwdFinal ff, BnBwdFinal fb) {
 // eval-mode BN folded to one multiply-add per element: y = x * scale + shift
 __global__ void bn_fold_kernel(const float* __restrict__ rm, const float* __restrict__ rv, const float* __restrict__ gamma,
                                const float* __restrict__ beta, int C, float eps, float* __restrict__ scale, float* __restrict__ shift) {
+  pdl_prologue();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float sc = gamma[c] * (1.0f / sqrtf(rv[c] + eps));
@@ -177,6 +179,7 @@ __global__ void bn_fold_kernel(const float* __restrict__ rm, const float* __rest
 
 __global__ void bn_eval_stats_kernel(const float* __restrict__ rm, const float* __restrict__ rv, int C, int G, float eps,
                                      float* __restrict__ mean, float* __restrict__ invstd) {
+  pdl_prologue();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float m = rm[c], is = 1.0f / sqrtf(rv[c] + eps);
@@ -187,6 +190,7 @@ constexpr int BN_EVAL_MAX_SEGS = 40;
 struct BnEvalSegs { BnEvalSeg s[BN_EVAL_MAX_SEGS]; int n; };
 // every BatchNorm of the network in one launch: blockIdx.y = BatchNorm, stats = [G][C] mean then [G][C] invstd
 __global__ void bn_eval_stats_all_kernel(const float* __restrict__ buffers, float* __restrict__ stats, BnEvalSegs segs, int G, float eps) {
+  pdl_prologue();
   const BnEvalSeg sg = segs.s[blockIdx.y];
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < sg.C; c += gridDim.x * blockDim.x) {
     const float m = buffers[sg.rm_off + c], is = 1.0f / sqrtf(buffers[sg.rv_off + c] + eps);
@@ -199,6 +203,7 @@ __global__ void bn_eval_stats_all_kernel(const float* __restrict__ buffers, floa
 
 __global__ void __launch_bounds__(BN_THREADS)
 bn_apply_kernel(BnApplyArgs a) {
+  pdl_prologue();
   extern __shared__ float sm[];   // per group: scale[C], mean[C], beta[C] (+ the same three of the residual's BatchNorm)
   const int C = a.C, G = a.G;
   const bool res_bn = a.r && a.rmean;
@@ -248,6 +253,7 @@ bn_apply_kernel(BnApplyArgs a) {
 // dx = gamma*invstd*(g - dbeta_g/Mg - xhat*dgamma_g/Mg)  (training)   |   gamma*invstd*g  (eval: frozen statistics)
 __global__ void __launch_bounds__(BN_THREADS)
 bn_bwd_apply_kernel(BnBwdArgs a) {
+  pdl_prologue();
   extern __shared__ float sm[];   // per group: k1[C], mean[C], invstd[C], dbeta/M[C], dgamma/M[C], scale[C], beta[C]
   const int C = a.C, G = a.G;
   const int64_t Mg = a.M / G;
@@ -306,6 +312,7 @@ stem_bn_relu_pool_kernel(const float* __restrict__ x, const float* __restrict__ 
                          const float* __restrict__ gamma, const float* __restrict__ beta,
                          float* __restrict__ y, uint8_t* __restrict__ argmax, __nv_bfloat16* __restrict__ y_hi,
                          __nv_bfloat16* __restrict__ y_lo, int N, int Hc, int Wc, int C, int Hp, int Wp, int imgs_per_group) {
+  pdl_prologue();
   const int q = C >> 2;
   const int64_t total = (int64_t)N * Hp * Wp * q;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -348,6 +355,7 @@ stem_pool_relu_bwd_kernel(const float* __restrict__ dyp, const uint8_t* __restri
                           const float* __restrict__ mean, const float* __restrict__ invstd,
                           const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ g,
                           int N, int Hc, int Wc, int C, int Hp, int Wp, int imgs_per_group) {
+  pdl_prologue();
   const int q = C >> 2;
   const int64_t total = (int64_t)N * Hc * Wc * q;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -458,7 +466,7 @@ int launch_bn_backward(const BnBwdArgs& a, cudaStream_t st) {
   BnFwdFinal ff = {};
   BnBwdFinal fb = {a.acc, a.sums, a.dgamma, a.dbeta, a.G, a.C};
   dim3 grid((unsigned)bn_colsum_blocks(Mg, a.C, a.G, resident), (unsigned)a.G);
-  DDN_LAUNCH(bn_colsum_kernel<1>, grid, BN_THREADS, 0, st, ca, ff, fb);
+  if (!a.sums_ready) DDN_LAUNCH(bn_colsum_kernel<1>, grid, BN_THREADS, 0, st, ca, ff, fb);
   const size_t smem = (size_t)a.G * 7 * a.C * sizeof(float);
   DDN_LAUNCH(bn_bwd_apply_kernel, ew_blocks(bn_bwd_apply_kernel, smem, a.M * (a.C / 4)), BN_THREADS, smem, st, a);
   return 0;

@@ -41,12 +41,39 @@ void set_error(const char* fmt, ...);
     if (r__ != 0) return r__;  \
   } while (0)
 
+// Programmatic dependent launch.  Every kernel of this library is launched with the programmatic-stream-serialization
+// attribute and starts with pdl_prologue(): `launch_dependents` lets the NEXT kernel's CTAs become resident as soon as an
+// SM has room for them (they park in `griddepcontrol.wait`, issuing nothing), and `wait` returns once the PREVIOUS kernel
+// has completed and its memory is visible.  A step is ~230 dependent launches; this removes the drain + launch gap between
+// them (and, in the persistent tcgen05 kernels, overlaps barrier init / TMEM allocation with the predecessor's tail).
+// Rule: nothing written by an earlier kernel may be read before pdl_wait(), and EVERY thread of every kernel executes it
+// (a kernel that skipped it could finish before its predecessor and break the chain for its successor).
+// DDN_PDL=0 launches without the attribute (the instructions are then no-ops).
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() { pdl_trigger(); pdl_wait(); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (pdl_enabled()) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // Every kernel launch goes through this so gpu_launches is an honest count.
-#define DDN_LAUNCH(kernel, grid, block, smem, stream, ...)         \
-  do {                                                             \
-    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);    \
-    ::ddn::g_launches.fetch_add(1, std::memory_order_relaxed);     \
-    DDN_CUDA(cudaGetLastError());                                  \
+#define DDN_LAUNCH(kernel, grid, block, smem, stream, ...)                                        \
+  do {                                                                                            \
+    DDN_CUDA(::ddn::launch_kernel(kernel, dim3(grid), dim3(block), (smem), (stream), __VA_ARGS__)); \
+    ::ddn::g_launches.fetch_add(1, std::memory_order_relaxed);                                    \
   } while (0)
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -58,6 +58,7 @@ struct BnBwdArgs {
   float* dgamma; float* dbeta;
   BnAccum acc; float* sums;       // workspace: accumulator (zero) and [G][2][C] floats
   int64_t M; int C; int relu; int training; int G;
+  int sums_ready;                 // the column sums are in `sums` already (written by a conv epilogue): skip that pass
 };
 int launch_bn_backward(const BnBwdArgs& a, cudaStream_t st);
 

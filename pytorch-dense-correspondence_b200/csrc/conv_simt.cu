@@ -19,6 +19,7 @@ namespace ddn {
 //                           dgrad:  wp[(r*KW+s)*Cout + co][CinP]  with (r,s) flipped
 __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restrict__ wp,
                                     int Cout, int Cin, int CinP, int KH, int KW, int dgrad) {
+  pdl_prologue();
   int64_t total = dgrad ? (int64_t)KH * KW * Cout * CinP : (int64_t)KH * KW * CinP * Cout;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int co, ci, r, s;
@@ -40,6 +41,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restri
 // dwp[(r*KW+s)*CinP + ci][Cout] -> dw[Cout][Cin][KH][KW]
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw,
                                     int Cout, int Cin, int CinP, int KH, int KW) {
+  pdl_prologue();
   int64_t total = (int64_t)Cout * Cin * KH * KW;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int s = (int)(i % KW); int64_t q = i / KW;
@@ -55,6 +57,7 @@ template <int BM, int BN, int BK, int TM, int TN>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 conv_gather_f32_kernel(const float* __restrict__ in, const float* __restrict__ wp, const float* __restrict__ addend,
                        float* __restrict__ out, ConvGeom g) {
+  pdl_prologue();
   constexpr int THREADS = (BM / TM) * (BN / TN);
   constexpr int A_F4 = BM * BK / 4;            // float4 loads per A tile
   constexpr int B_F4 = BK * BN / 4;
@@ -198,6 +201,7 @@ template <int BKR, int BN, int BP, int TM, int TN>   // BKR rows of K, BN cols o
 __global__ void __launch_bounds__((BKR / TM) * (BN / TN))
 conv_wgrad_f32_kernel(const float* __restrict__ in, const float* __restrict__ dy, float* __restrict__ dwp,
                       ConvGeom g, int pixels_per_split) {
+  pdl_prologue();
   constexpr int THREADS = (BKR / TM) * (BN / TN);
   constexpr int A_F4 = BP * BKR / 4, B_F4 = BP * BN / 4;
   constexpr int A_PER_T = A_F4 / THREADS, B_PER_T = B_F4 / THREADS;

@@ -69,6 +69,9 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -123,6 +126,26 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// Whole-warp variants: all 32 lanes run the (warp-uniform) issue loop and ONE elected lane issues the instruction.  With the loop
+// uniform the descriptors live in uniform registers and an MMA costs ~3 issue slots instead of the ~9 (R2UR + ELECT loop) the
+// compiler needs when a single lane runs the loop -- which matters when an MMA is only 32 tensor-core cycles (N = 64).
+__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}\n" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -170,6 +193,7 @@ struct TcConvParams {
   int full_items, tail_split, total_items;
   int imgs_per_group;    // BatchNorm group of image n = n / imgs_per_group
   BnFwdFinal fin;        // fin.a.acc == nullptr: no statistics
+  TcBwdStats bst;        // bst.fin.a.acc != nullptr (data gradient): column sums of the BatchNorm backward that consumes `out`
   // optional folded epilogue (inference): y = relu?(acc * ep_scale[c] + ep_shift[c] + addend)
   const float* ep_scale; const float* ep_shift; int ep_relu;
   __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
@@ -241,6 +265,28 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {     // arrives 
                ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
+// In-register transpose inside each group of 8 lanes.  In: lane 8a+b holds v[4j .. 4j+3] = elements (row 8a+b, columns 4j ..
+// 4j+3), j = 0..7 (what tcgen05.ld.32x32b.x32 delivers: one accumulator row per lane).  Out: v[4i .. 4i+3] = (row 8a+i, columns
+// 4b .. 4b+3).  After it the 8 lanes of a group hold the 8 column quads of ONE row for every i, so a 128-bit load / store per
+// lane moves whole 128-byte lines of NHWC memory (4 lines per warp instruction instead of 32 partial ones -- the row-per-lane
+// epilogue was bound by exactly that), and a column sum is 8 local adds + 2 shuffle stages.  3 butterfly stages, 48 shuffles.
+__device__ __forceinline__ void transpose_8x8_quads(uint32_t (&v)[32], int lane) {
+#pragma unroll
+  for (int k = 1; k < 8; k <<= 1) {
+    const bool up = (lane & k) != 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j & k) continue;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const uint32_t send = up ? v[4 * j + t] : v[4 * (j | k) + t];
+        const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, k);
+        if (up) v[4 * j + t] = recv; else v[4 * (j | k) + t] = recv;
+      }
+    }
+  }
+}
+
 struct TcItem { int sp, co0, width; };
 __device__ __forceinline__ TcItem tc_item(const TcConvParams& p, int idx, int block_n) {
   int tile = idx, piece = 0, width = block_n;
@@ -293,8 +339,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   __shared__ __align__(8) uint64_t acc_empty[2];         // PAIR: used in the leader only
   __shared__ uint32_t tmem_base_smem;
   __shared__ int s_last;
-  __shared__ float s_part[2][2][4][BLOCK_N];             // [accumulator][sum | sum of squares][epilogue warp][column]
+  __shared__ __align__(16) float s_part[2][2][4][BLOCK_N];            // [accumulator][sum | sum of squares][epilogue warp][column]
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = PAIR ? cluster_cta_rank() : 0u;
   const bool leader = rank == 0;
@@ -325,6 +372,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   if (PAIR) cluster_sync_all();    // the peer's barriers are initialised before anything can arrive on them
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();                      // everything above overlapped the previous kernel's tail; its results are visible from here
 
   if (warp == 0) {
     // ===== TMA producer (PAIR: both CTAs; own two sub-tiles of A + own half of the B rows, signalled on the leader's barrier)
@@ -424,74 +472,127 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     }
   } else {
     // ===== epilogue warps (PAIR: of both CTAs): own 128 pixels x width channels from the local TMEM =====
+    // tcgen05.ld hands every lane one accumulator ROW (pixel); transpose_8x8_quads turns that into "8 lanes = the 8 channel quads of
+    // one pixel", so every global access below is a whole 128-byte line per 8 lanes and per-channel constants are one load per lane.
     const int q = warp & 3;                          // TMEM lane quarter this warp may read
     const int e = threadIdx.x - 64;                  // 0..127
-    const int sub_row = (q & 1) * 32 + lane;         // row inside this warp's sub-tile
+    const int ga = lane >> 3, gb = lane & 7;         // after the transpose: lane 8a+b = channel quad b of rows 32(q&1) + 8a + i, i = 0..7
     const bool stats = p.fin.a.acc != nullptr;
+    const bool bstats = p.bst.fin.a.acc != nullptr;
+    double* const sum_acc = bstats ? p.bst.fin.a.acc : p.fin.a.acc;
     int k_it = 0;
     for (int idx = worker; idx < p.total_items; idx += n_workers, ++k_it) {
       const TcItem it = tc_item(p, idx, BLOCK_N);
       const int buf = k_it & 1;
       const int st0 = it.sp * SUBS_PER_TILE + (PAIR ? 2 * (int)rank : 0);
       const TcSub sb = tc_sub(p, st0 + (q >> 1));
-      const int h = sb.h0 + sub_row / TC_SUB_W, w = sb.w0 + sub_row % TC_SUB_W;
-      const bool ok = sb.valid && h < p.H && w < p.W;
-      const size_t pix = ((size_t)(ok ? sb.n : 0) * p.H + (ok ? h : 0)) * p.W + (ok ? w : 0);
-      float* o = p.out + pix * p.Cout + it.co0;
-      const float* ad = p.addend ? p.addend + pix * p.Cout + it.co0 : nullptr;
+      // rows 8a .. 8a+7 of this warp's half sub-tile: image row h, columns w8 .. w8 + 7
+      const int h = sb.h0 + 2 * (q & 1) + (ga >> 1), w8 = sb.w0 + 8 * (ga & 1);
+      const int n_ok = (sb.valid && h < p.H) ? min(8, p.W - w8) : 0;          // valid pixels among the 8 (<= 0: none)
+      const size_t pix = ((size_t)(n_ok > 0 ? sb.n : 0) * p.H + (n_ok > 0 ? h : 0)) * p.W + (n_ok > 0 ? w8 : 0);
+      const size_t cbase = pix * p.Cout + it.co0 + gb * 4;                     // + i * Cout + c * 32
+      const int grp = n_ok > 0 ? sb.n / p.imgs_per_group : 0;
       mbar_wait(smem_u32(&acc_full[buf]), (k_it >> 1) & 1);
       tc_fence_after();
       const int n_chunks = it.width >> 5;
 #pragma unroll 1
       for (int c = 0; c < n_chunks; ++c) {
+        const size_t coff = cbase + c * 32;
         // the addend (residual-branch gradient) of this chunk first: its global-load latency overlaps the TMEM read
         float4 adv[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          adv[j] = (ad && ok) ? __ldg(reinterpret_cast<const float4*>(ad + c * 32) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 8; ++i)
+          adv[i] = (p.addend && i < n_ok) ? __ldg(reinterpret_cast<const float4*>(p.addend + coff + (size_t)i * p.Cout)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        // backward statistics: the pre-BatchNorm activation (and the sign plane of the block output) of the same elements
+        float4 rw[8];
+        uint2 yh[8];
+        if (bstats) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            rw[i] = i < n_ok ? __ldg(reinterpret_cast<const float4*>(p.bst.raw + coff + (size_t)i * p.Cout)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bst.y_hi) yh[i] = i < n_ok ? __ldg(reinterpret_cast<const uint2*>(p.bst.y_hi + coff + (size_t)i * p.Cout)) : make_uint2(0u, 0u);
+          }
+        }
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BLOCK_N + c * 32), v);
+        transpose_8x8_quads(v, lane);
+        float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;      // column sums of this lane's 8 rows (4 channels)
         if (p.ep_scale) {        // folded BatchNorm (+ residual, ReLU): the conv output never exists un-normalised
-          const float4* sc = reinterpret_cast<const float4*>(p.ep_scale + it.co0 + c * 32);
-          const float4* sh = reinterpret_cast<const float4*>(p.ep_shift + it.co0 + c * 32);
-          uint32_t hp[16], lp[16];
+          const float4 sc = __ldg(reinterpret_cast<const float4*>(p.ep_scale + it.co0 + c * 32 + gb * 4));
+          const float4 sh = __ldg(reinterpret_cast<const float4*>(p.ep_shift + it.co0 + c * 32 + gb * 4));
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 a = __ldg(sc + j), b = __ldg(sh + j);
-            float4 f = make_float4(fmaf(__uint_as_float(v[4 * j]), a.x, b.x) + adv[j].x, fmaf(__uint_as_float(v[4 * j + 1]), a.y, b.y) + adv[j].y,
-                                   fmaf(__uint_as_float(v[4 * j + 2]), a.z, b.z) + adv[j].z, fmaf(__uint_as_float(v[4 * j + 3]), a.w, b.w) + adv[j].w);
+          for (int i = 0; i < 8; ++i) {
+            float4 f = make_float4(fmaf(__uint_as_float(v[4 * i]), sc.x, sh.x) + adv[i].x, fmaf(__uint_as_float(v[4 * i + 1]), sc.y, sh.y) + adv[i].y,
+                                   fmaf(__uint_as_float(v[4 * i + 2]), sc.z, sh.z) + adv[i].z, fmaf(__uint_as_float(v[4 * i + 3]), sc.w, sh.w) + adv[i].w);
             if (p.ep_relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f); }
-            if (ok && p.out) reinterpret_cast<float4*>(o + c * 32)[j] = f;
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(f.x), h1 = __float2bfloat16_rn(f.y), h2 = __float2bfloat16_rn(f.z), h3 = __float2bfloat16_rn(f.w);
-            hp[2 * j] = pack_bf16x2(h0, h1); hp[2 * j + 1] = pack_bf16x2(h2, h3);
-            lp[2 * j] = pack_bf16x2(__float2bfloat16_rn(f.x - __bfloat162float(h0)), __float2bfloat16_rn(f.y - __bfloat162float(h1)));
-            lp[2 * j + 1] = pack_bf16x2(__float2bfloat16_rn(f.z - __bfloat162float(h2)), __float2bfloat16_rn(f.w - __bfloat162float(h3)));
-          }
-          if (ok && p.out_hi) {
-            uint4* oh = reinterpret_cast<uint4*>(p.out_hi + pix * p.Cout + it.co0 + c * 32);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) oh[j] = make_uint4(hp[4 * j], hp[4 * j + 1], hp[4 * j + 2], hp[4 * j + 3]);
-            if (p.out_lo) {
-              uint4* ol = reinterpret_cast<uint4*>(p.out_lo + pix * p.Cout + it.co0 + c * 32);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) ol[j] = make_uint4(lp[4 * j], lp[4 * j + 1], lp[4 * j + 2], lp[4 * j + 3]);
+            if (i < n_ok) {
+              if (p.out) *reinterpret_cast<float4*>(p.out + coff + (size_t)i * p.Cout) = f;
+              if (p.out_hi) {
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(f.x), h1 = __float2bfloat16_rn(f.y), h2 = __float2bfloat16_rn(f.z), h3 = __float2bfloat16_rn(f.w);
+                *reinterpret_cast<uint2*>(p.out_hi + coff + (size_t)i * p.Cout) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+                if (p.out_lo)
+                  *reinterpret_cast<uint2*>(p.out_lo + coff + (size_t)i * p.Cout) =
+                      make_uint2(pack_bf16x2(__float2bfloat16_rn(f.x - __bfloat162float(h0)), __float2bfloat16_rn(f.y - __bfloat162float(h1))),
+                                 pack_bf16x2(__float2bfloat16_rn(f.z - __bfloat162float(h2)), __float2bfloat16_rn(f.w - __bfloat162float(h3))));
+              }
             }
           }
-        } else if (ok) {
+        } else if (bstats) {
+          // g = dOut * (y > 0), (sum g, sum g * xhat): what bn_colsum_kernel<1> computes, on the gradient this kernel just wrote
+          const float4 mu = __ldg(reinterpret_cast<const float4*>(p.bst.mean + (size_t)grp * p.Cout + it.co0 + c * 32 + gb * 4));
+          const float4 is = __ldg(reinterpret_cast<const float4*>(p.bst.invstd + (size_t)grp * p.Cout + it.co0 + c * 32 + gb * 4));
+          float4 scl = make_float4(0.f, 0.f, 0.f, 0.f), be = scl;
+          if (!p.bst.y_hi && p.bst.relu) {     // no residual in the forward: y > 0 <=> bn(x) > 0, the same fmaf as bn_apply_kernel
+            const float4 gm = __ldg(reinterpret_cast<const float4*>(p.bst.gamma + it.co0 + c * 32 + gb * 4));
+            be = __ldg(reinterpret_cast<const float4*>(p.bst.beta + it.co0 + c * 32 + gb * 4));
+            scl = make_float4(gm.x * is.x, gm.y * is.y, gm.z * is.z, gm.w * is.w);
+          }
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            reinterpret_cast<float4*>(o + c * 32)[j] =
-                make_float4(__uint_as_float(v[4 * j]) + adv[j].x, __uint_as_float(v[4 * j + 1]) + adv[j].y,
-                            __uint_as_float(v[4 * j + 2]) + adv[j].z, __uint_as_float(v[4 * j + 3]) + adv[j].w);
+          for (int i = 0; i < 8; ++i) {
+            float4 g = make_float4(__uint_as_float(v[4 * i]) + adv[i].x, __uint_as_float(v[4 * i + 1]) + adv[i].y,
+                                   __uint_as_float(v[4 * i + 2]) + adv[i].z, __uint_as_float(v[4 * i + 3]) + adv[i].w);
+            if (i < n_ok) *reinterpret_cast<float4*>(p.out + coff + (size_t)i * p.Cout) = g;
+            else g = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bst.y_hi) {
+              const uint2 hh = yh[i];
+              if ((hh.x & 0x8000u) || !(hh.x & 0x7fffu)) g.x = 0.f;
+              if ((hh.x & 0x80000000u) || !(hh.x & 0x7fff0000u)) g.y = 0.f;
+              if ((hh.y & 0x8000u) || !(hh.y & 0x7fffu)) g.z = 0.f;
+              if ((hh.y & 0x80000000u) || !(hh.y & 0x7fff0000u)) g.w = 0.f;
+            } else if (p.bst.relu) {
+              if (!(fmaf(rw[i].x - mu.x, scl.x, be.x) > 0.f)) g.x = 0.f;
+              if (!(fmaf(rw[i].y - mu.y, scl.y, be.y) > 0.f)) g.y = 0.f;
+              if (!(fmaf(rw[i].z - mu.z, scl.z, be.z) > 0.f)) g.z = 0.f;
+              if (!(fmaf(rw[i].w - mu.w, scl.w, be.w) > 0.f)) g.w = 0.f;
+            }
+            s1.x += g.x; s1.y += g.y; s1.z += g.z; s1.w += g.w;
+            s2.x = fmaf(g.x, (rw[i].x - mu.x) * is.x, s2.x); s2.y = fmaf(g.y, (rw[i].y - mu.y) * is.y, s2.y);
+            s2.z = fmaf(g.z, (rw[i].z - mu.z) * is.z, s2.z); s2.w = fmaf(g.w, (rw[i].w - mu.w) * is.w, s2.w);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            // rows outside the image hold garbage (their shifted taps can read valid pixels): neither stored nor summed
+            const float4 raw = i < n_ok ? make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < n_ok)
+              *reinterpret_cast<float4*>(p.out + coff + (size_t)i * p.Cout) = make_float4(raw.x + adv[i].x, raw.y + adv[i].y, raw.z + adv[i].z, raw.w + adv[i].w);
+            s1.x += raw.x; s1.y += raw.y; s1.z += raw.z; s1.w += raw.w;
+            s2.x = fmaf(raw.x, raw.x, s2.x); s2.y = fmaf(raw.y, raw.y, s2.y); s2.z = fmaf(raw.z, raw.z, s2.z); s2.w = fmaf(raw.w, raw.w, s2.w);
+          }
         }
-        if (stats) {      // rows outside the image hold garbage (their shifted taps can read valid pixels): mask
-          float a[32], b[32];
+        if (stats || bstats) {      // the other 24 rows of this warp sit in lanes b + 8, b + 16, b + 24
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { a[j] = ok ? __uint_as_float(v[j]) : 0.f; b[j] = a[j] * a[j]; }
-          warp_colsum32(a, lane);
-          warp_colsum32(b, lane);
-          s_part[buf][0][q][c * 32 + lane] = a[0];
-          s_part[buf][1][q][c * 32 + lane] = b[0];
+          for (int off = 8; off < 32; off <<= 1) {
+            s1.x += __shfl_xor_sync(0xffffffffu, s1.x, off); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, off);
+            s1.z += __shfl_xor_sync(0xffffffffu, s1.z, off); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, off);
+            s2.x += __shfl_xor_sync(0xffffffffu, s2.x, off); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, off);
+            s2.z += __shfl_xor_sync(0xffffffffu, s2.z, off); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, off);
+          }
+          if (ga == 0) {
+            *reinterpret_cast<float4*>(&s_part[buf][0][q][c * 32 + gb * 4]) = s1;
+            *reinterpret_cast<float4*>(&s_part[buf][1][q][c * 32 + gb * 4]) = s2;
+          }
         }
       }
       // the accumulator is in registers / memory now: hand the TMEM buffer back to the MMA warp
@@ -501,21 +602,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         if (PAIR) mbar_arrive_cluster(smem_u32(&acc_empty[buf]), 0);     // 4 warps x 2 CTAs release the leader's MMA thread
         else mbar_arrive(smem_u32(&acc_empty[buf]));
       }
-      if (stats) {
+      if (stats || bstats) {
         asm volatile("bar.sync 1, 128;" ::: "memory");          // the 4 epilogue warps only
         // warps 0,1 hold sub-tile A, warps 2,3 sub-tile B; their images may belong to different BatchNorm groups
         const TcSub sa = tc_sub(p, st0), sbb = tc_sub(p, st0 + 1);
-        const int ga = sa.valid ? sa.n / p.imgs_per_group : -1, gb = sbb.valid ? sbb.n / p.imgs_per_group : -1;
+        const int ga_ = sa.valid ? sa.n / p.imgs_per_group : -1, gb_ = sbb.valid ? sbb.n / p.imgs_per_group : -1;
         for (int col = e; col < it.width; col += 128) {
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
             const float va = s_part[buf][k][0][col] + s_part[buf][k][1][col];
             const float vb = s_part[buf][k][2][col] + s_part[buf][k][3][col];
-            if (ga >= 0 && ga == gb) {
-              red_add_f64(p.fin.a.acc + (size_t)(ga * 2 + k) * p.Cout + it.co0 + col, (double)va + (double)vb);
+            if (ga_ >= 0 && ga_ == gb_) {
+              red_add_f64(sum_acc + (size_t)(ga_ * 2 + k) * p.Cout + it.co0 + col, (double)va + (double)vb);
             } else {
-              if (ga >= 0) red_add_f64(p.fin.a.acc + (size_t)(ga * 2 + k) * p.Cout + it.co0 + col, (double)va);
-              if (gb >= 0) red_add_f64(p.fin.a.acc + (size_t)(gb * 2 + k) * p.Cout + it.co0 + col, (double)vb);
+              if (ga_ >= 0) red_add_f64(sum_acc + (size_t)(ga_ * 2 + k) * p.Cout + it.co0 + col, (double)va);
+              if (gb_ >= 0) red_add_f64(sum_acc + (size_t)(gb_ * 2 + k) * p.Cout + it.co0 + col, (double)vb);
             }
           }
         }
@@ -526,6 +627,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       const bool last = bn_last_cta(p.fin.a.ticket, gridDim.x, e == 0, &s_last, [] { asm volatile("bar.sync 1, 128;" ::: "memory"); });
       if (last)
         for (int c = e; c < p.Cout; c += 128) bn_fwd_finalize_channel(p.fin, c);
+    } else if (bstats) {   // ... or into dgamma / dbeta and the per-group sums bn_bwd_apply_kernel reads
+      const bool last = bn_last_cta(p.bst.fin.a.ticket, gridDim.x, e == 0, &s_last, [] { asm volatile("bar.sync 1, 128;" ::: "memory"); });
+      if (last)
+        for (int c = e; c < p.Cout; c += 128) bn_bwd_finalize_channel(p.bst.fin, c);
     }
   }
   tc_fence_before();
@@ -535,6 +640,259 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     tc_fence_after();
     if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(NCOLS));
     else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(NCOLS));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ 64 -> 64 channels: halo tiles
+// The 3x3 convolutions of layer1 (64 -> 64 channels on the 120x160 map) have the lowest arithmetic intensity of the network:
+// with one TMA box per (tap, tile) every 128-pixel tile pulls 9 x 32 KB of activations and the whole 147 KB weight tensor
+// through L2 -> shared memory, ~1 GB per convolution, and the kernel above runs at the L2-to-SM throughput cap (~110 us for
+// a convolution with 30 us of tensor-core work).  This kernel loads every operand ONCE:
+//   * the weights (9 taps x [64 co x 64 ci], hi and lo planes, 147 KB) stay resident in shared memory for the whole launch;
+//   * a tile is 8 rows x 16 columns of output pixels; its 10 x 18 HALO (one TMA box per plane, out-of-bounds = padding) is
+//     staged once and all 9 taps read it in place.  The tensor map has H and W swapped, so halo pixel (h, w) is shared-memory
+//     row w * 10 + h: MMA row m = 8 * (m / 8) + m % 8 is output pixel (h0 + m % 8, w0 + m / 8), the 8 rows of a core-matrix
+//     group are 8 consecutive halo rows, consecutive groups are 10 rows apart (SBO = 1280 B), and tap (r, s) is the same
+//     window shifted by (s * 10 + r) rows.  tcgen05 applies the 128-byte swizzle to absolute shared-memory address bits, so
+//     a descriptor may start at any 128-byte row of the staged tile (base-offset field 0; scripts/probe_umma_offset.cu
+//     checks exactly this on the hardware).
+// bf16x3 order: first the 72 MMAs that read the hi plane of the tile (hi*lo + hi*hi), then the 36 that read the lo plane, so a
+// ring of 3 plane slots always has the next plane in flight.  L2 -> SM traffic per convolution: ~110 MB instead of ~1 GB.
+struct TcHaloParams {
+  float* out; const float* addend;
+  int N, H, W;
+  int tiles_h, tiles_w, n_tiles;
+  int imgs_per_group;
+  BnFwdFinal fin;
+};
+constexpr int HALO_TH = 8, HALO_TW = 16;
+constexpr int HALO_BH = HALO_TH + 2, HALO_BW = HALO_TW + 2;
+constexpr int HALO_BOX_BYTES = HALO_BH * HALO_BW * 128;                      // 23,040
+constexpr int HALO_SLOT = ((HALO_BOX_BYTES + 1023) / 1024) * 1024;           // 23,552
+constexpr int HALO_SLOTS = 3;
+constexpr int HALO_B_TAP = 64 * 128;                                         // one tap: 64 co x 64 ci bf16
+constexpr int HALO_B_PLANE = 9 * HALO_B_TAP;
+
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int NPROD>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv64_halo_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, const TcHaloParams p) {
+  constexpr int NSPLIT = NPROD == 3 ? 2 : 1;
+  constexpr int NCOLS = 128;                                // two 64-column accumulators
+  constexpr uint32_t IDESC = make_idesc_bf16(128, 64);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_b = smem;                                   // [plane][tap][64 x 128 B]
+  uint8_t* smem_a = smem + NSPLIT * HALO_B_PLANE;           // HALO_SLOTS plane slots
+  __shared__ __align__(8) uint64_t full_bar[HALO_SLOTS], empty_bar[HALO_SLOTS], acc_full[2], acc_empty[2], b_full;
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ int s_last;
+  __shared__ __align__(16) float s_part[2][2][4][64];
+
+  pdl_trigger();
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < HALO_SLOTS; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&acc_full[b]), 1); mbar_init(smem_u32(&acc_empty[b]), 4); }
+    mbar_init(smem_u32(&b_full), 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_b_hi);
+    if (NSPLIT == 2) { tma_prefetch_desc(&tm_a_lo); tma_prefetch_desc(&tm_b_lo); }
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(NCOLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();
+
+  auto tile_of = [&](int t, int& n, int& h0, int& w0) {
+    const int tw = t % p.tiles_w; const int q = t / p.tiles_w;
+    const int th = q % p.tiles_h; n = q / p.tiles_h;
+    h0 = th * HALO_TH; w0 = tw * HALO_TW;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t bb = smem_u32(&b_full);
+      mbar_expect_tx(bb, NSPLIT * HALO_B_PLANE);
+#pragma unroll 1
+      for (int tap = 0; tap < 9; ++tap) {
+        tma_load_2d(smem_u32(smem_b + tap * HALO_B_TAP), &tm_b_hi, bb, tap * 64, 0);
+        if (NSPLIT == 2) tma_load_2d(smem_u32(smem_b + HALO_B_PLANE + tap * HALO_B_TAP), &tm_b_lo, bb, tap * 64, 0);
+      }
+      uint32_t g = 0;
+      // the ring holds 1.5 tiles: far enough ahead for an L2 hit, not for a DRAM miss -- so the halos of the tiles two and three
+      // rounds ahead are pulled into L2 by prefetches that occupy no shared memory
+      constexpr int PF = 2;
+      for (int j = 0; j < PF; ++j) {
+        const int tp = blockIdx.x + j * gridDim.x;
+        if (tp < p.n_tiles) {
+          int n, h0, w0;
+          tile_of(tp, n, h0, w0);
+          tma_prefetch_l2_4d(&tm_a_hi, 0, h0 - 1, w0 - 1, n);
+          if (NSPLIT == 2) tma_prefetch_l2_4d(&tm_a_lo, 0, h0 - 1, w0 - 1, n);
+        }
+      }
+      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        int n, h0, w0;
+        {
+          const int tp = t + PF * gridDim.x;
+          if (tp < p.n_tiles) {
+            tile_of(tp, n, h0, w0);
+            tma_prefetch_l2_4d(&tm_a_hi, 0, h0 - 1, w0 - 1, n);
+            if (NSPLIT == 2) tma_prefetch_l2_4d(&tm_a_lo, 0, h0 - 1, w0 - 1, n);
+          }
+        }
+        tile_of(t, n, h0, w0);
+#pragma unroll
+        for (int pl = 0; pl < NSPLIT; ++pl, ++g) {
+          const int s = g % HALO_SLOTS;
+          mbar_wait(smem_u32(&empty_bar[s]), ((g / HALO_SLOTS) & 1) ^ 1);
+          const uint32_t bar = smem_u32(&full_bar[s]);
+          mbar_expect_tx(bar, HALO_BOX_BYTES);
+          tma_load_4d(smem_u32(smem_a + s * HALO_SLOT), pl == 0 ? &tm_a_hi : &tm_a_lo, bar, 0, h0 - 1, w0 - 1, n);   // map dims: {c, h, w, n}
+        }
+      }
+    }
+  } else if (warp == 1) {
+    {   // the whole warp walks the issue loop (see umma_bf16_elect)
+      mbar_wait(smem_u32(&b_full), 0);
+      tc_fence_after();
+      const uint64_t bd_hi = make_kmajor_desc<TC_BLOCK_K>(smem_u32(smem_b));
+      const uint64_t bd_lo = make_kmajor_desc<TC_BLOCK_K>(smem_u32(smem_b + HALO_B_PLANE));
+      uint32_t g = 0;
+      int k_it = 0;
+      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++k_it) {
+        const int buf = k_it & 1;
+        mbar_wait(smem_u32(&acc_empty[buf]), ((k_it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)(buf * 64);
+        // The issuing thread has 32 tensor-core cycles per N = 64 MMA: every descriptor below is `base + compile-time constant`
+        // (taps and k-steps fully unrolled), ~4 instructions per MMA.
+        {   // plane hi of the tile: hi*lo + hi*hi (bf16x3) or hi*hi
+          const int s = g % HALO_SLOTS;
+          mbar_wait(smem_u32(&full_bar[s]), (g / HALO_SLOTS) & 1);
+          tc_fence_after();
+          const uint64_t a0 = make_kmajor_sw128_desc_sbo(smem_u32(smem_a + s * HALO_SLOT), HALO_BH * 128);
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ad = a0 + (uint64_t)((((tap % 3) * HALO_BH + tap / 3) * 128 + k * 32) >> 4);
+              const uint64_t boff = (uint64_t)((tap * HALO_B_TAP + k * 32) >> 4);
+              if (NPROD == 3) {
+                umma_bf16_elect(acc, ad, bd_lo + boff, IDESC, (tap | k) != 0);
+                umma_bf16_elect(acc, ad, bd_hi + boff, IDESC, 1);
+              } else {
+                umma_bf16_elect(acc, ad, bd_hi + boff, IDESC, (tap | k) != 0);
+              }
+            }
+          }
+          umma_commit_elect(smem_u32(&empty_bar[s]));
+          ++g;
+        }
+        if (NPROD == 3) {   // plane lo: lo*hi
+          const int s = g % HALO_SLOTS;
+          mbar_wait(smem_u32(&full_bar[s]), (g / HALO_SLOTS) & 1);
+          tc_fence_after();
+          const uint64_t a0 = make_kmajor_sw128_desc_sbo(smem_u32(smem_a + s * HALO_SLOT), HALO_BH * 128);
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_elect(acc, a0 + (uint64_t)((((tap % 3) * HALO_BH + tap / 3) * 128 + k * 32) >> 4),
+                        bd_hi + (uint64_t)((tap * HALO_B_TAP + k * 32) >> 4), IDESC, 1);
+          }
+          umma_commit_elect(smem_u32(&empty_bar[s]));
+          ++g;
+        }
+        umma_commit_elect(smem_u32(&acc_full[buf]));
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int e = threadIdx.x - 64;
+    const int ga = lane >> 3, gb = lane & 7;           // after the transpose: lane 8a+b holds rows 32q + 8a + i, channel quad b
+    const bool stats = p.fin.a.acc != nullptr;
+    int k_it = 0;
+    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++k_it) {
+      const int buf = k_it & 1;
+      int n, h0, w0;
+      tile_of(t, n, h0, w0);
+      // MMA row m = 32q + 8a + i is output pixel (h0 + i, w0 + 4q + a): the tiles are whole (H % 8 == 0, W % 16 == 0)
+      const size_t pix0 = ((size_t)n * p.H + h0) * p.W + (w0 + 4 * q + ga);
+      const size_t row_stride = (size_t)p.W * 64;      // floats between (h, w) and (h + 1, w)
+      float* o = p.out + pix0 * 64 + gb * 4;
+      const float* ad = p.addend ? p.addend + pix0 * 64 + gb * 4 : nullptr;
+      mbar_wait(smem_u32(&acc_full[buf]), (k_it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        float4 adv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          adv[i] = ad ? __ldg(reinterpret_cast<const float4*>(ad + i * row_stride + c * 32)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 64 + c * 32), v);
+        transpose_8x8_quads(v, lane);
+        float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 raw = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+          *reinterpret_cast<float4*>(o + i * row_stride + c * 32) = make_float4(raw.x + adv[i].x, raw.y + adv[i].y, raw.z + adv[i].z, raw.w + adv[i].w);
+          s1.x += raw.x; s1.y += raw.y; s1.z += raw.z; s1.w += raw.w;
+          s2.x = fmaf(raw.x, raw.x, s2.x); s2.y = fmaf(raw.y, raw.y, s2.y); s2.z = fmaf(raw.z, raw.z, s2.z); s2.w = fmaf(raw.w, raw.w, s2.w);
+        }
+        if (stats) {      // 8 rows summed locally; the other 24 rows of this warp sit in lanes b + 8, b + 16, b + 24
+#pragma unroll
+          for (int off = 8; off < 32; off <<= 1) {
+            s1.x += __shfl_xor_sync(0xffffffffu, s1.x, off); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, off);
+            s1.z += __shfl_xor_sync(0xffffffffu, s1.z, off); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, off);
+            s2.x += __shfl_xor_sync(0xffffffffu, s2.x, off); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, off);
+            s2.z += __shfl_xor_sync(0xffffffffu, s2.z, off); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, off);
+          }
+          if (ga == 0) {
+            *reinterpret_cast<float4*>(&s_part[buf][0][q][c * 32 + gb * 4]) = s1;
+            *reinterpret_cast<float4*>(&s_part[buf][1][q][c * 32 + gb * 4]) = s2;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
+      if (stats) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int grp = n / p.imgs_per_group;          // a tile lies inside one image
+        const int col = e & 63, k = e >> 6;            // 128 threads = 64 columns x {sum, sum of squares}
+        const float s4 = s_part[buf][k][0][col] + s_part[buf][k][1][col] + s_part[buf][k][2][col] + s_part[buf][k][3][col];
+        red_add_f64(p.fin.a.acc + (size_t)(grp * 2 + k) * 64 + col, (double)s4);
+      }
+    }
+    if (stats) {
+      const bool last = bn_last_cta(p.fin.a.ticket, gridDim.x, e == 0, &s_last, [] { asm volatile("bar.sync 1, 128;" ::: "memory"); });
+      if (last)
+        for (int c = e; c < 64; c += 128) bn_fwd_finalize_channel(p.fin, c);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(NCOLS));
   }
 }
 
@@ -587,6 +945,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_const
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_base_smem;
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ci_tiles = p.Cin / BN;
   const int ci0 = (blockIdx.x % ci_tiles) * BN;
@@ -614,6 +973,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();
 
   if (num_kb > 0) {
     if (warp == 0) {
@@ -717,8 +1077,150 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_const
   }
 }
 
+// ------------------------------------------------------------------------------------------------ 64 -> 64 weight gradient: halo tiles
+// The kernel above gives a 64 x 64 convolution (layer1) half-empty MMAs (128 accumulator rows for 64 output channels) and, with one
+// X box per (tap, 64 pixels), ~1.1 GB of L2 -> shared-memory traffic per weight gradient: it runs at the L2 throughput cap, 150 us
+// for 35 us of tensor-core work.  Here a CTA walks 8 x 16-pixel tiles (the geometry and the H/W-swapped tensor maps of
+// conv64_halo_kernel); per tile it stages the 10 x 18 halo of X and the 8 x 16 tile of dY ONCE, and
+//   * the roles are swapped: the M side is X, shifted, with TWO TAPS STACKED along M -- the second 64-channel atom of the
+//     MN-major A descriptor is the same staged halo shifted by the distance between the two taps (LBO = that many 128-byte rows;
+//     scripts/probe_umma_offset.cu, "MN-stack") -- and the N side is dY (64 output channels);
+//   * 9 taps = 5 accumulators of [2 taps x 64 ci] x [64 co] fp32 in TMEM (the 5th pairs tap 8 with itself), kept for the whole
+//     launch; K = pixels, 16 per MMA = two columns of 8 rows (SBO = 10 halo rows for X, 8 rows for dY).
+// At the end each CTA adds its partial dW into dwp[tap][co][ci] (warp-coalesced fp32 reds).
+struct TcWgradHaloParams {
+  float* dwp;            // [9][64][64] fp32, zero-filled by the caller
+  int N, H, W;
+  int tiles_h, tiles_w, n_tiles;
+};
+constexpr int WGH_X_SLOT = HALO_SLOT;                    // 10 x 18 halo of X, one plane
+constexpr int WGH_DY_BYTES = 128 * 128;                  // 8 x 16 pixels x 64 channels, one plane
+constexpr int WGH_PAIRS = 5;
+__host__ __device__ constexpr int wgh_tap_a(int pr) { return pr == 0 ? 0 : pr == 1 ? 6 : pr == 2 ? 4 : pr == 3 ? 2 : 8; }   // lower halo offset
+__host__ __device__ constexpr int wgh_tap_b(int pr) { return pr == 0 ? 3 : pr == 1 ? 1 : pr == 2 ? 7 : pr == 3 ? 5 : 8; }
+__host__ __device__ constexpr int wgh_off(int tap) { return (tap % 3) * HALO_BH + tap / 3; }       // halo row of tap (r, s) = s * 10 + r
+
+template <int NPROD>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+wgrad64_halo_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
+                    const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_constant__ CUtensorMap tm_dy_lo, const TcWgradHaloParams p) {
+  constexpr int NSPLIT = NPROD == 3 ? 2 : 1;
+  constexpr int STAGE = NSPLIT * (WGH_X_SLOT + WGH_DY_BYTES);
+  constexpr int STAGES = 2;
+  constexpr int NCOLS = 512;                                // 5 x 64 accumulator columns
+  constexpr uint32_t IDESC = make_idesc_bf16_mn(128, 64);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], done_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  pdl_trigger();
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    mbar_init(smem_u32(&done_bar), 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_x_hi); tma_prefetch_desc(&tm_dy_hi);
+    if (NSPLIT == 2) { tma_prefetch_desc(&tm_x_lo); tma_prefetch_desc(&tm_dy_lo); }
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(NCOLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();
+  const int my_tiles = p.n_tiles > (int)blockIdx.x ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int i = 0;
+      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++i) {
+        const int tw = t % p.tiles_w; const int q = t / p.tiles_w;
+        const int th = q % p.tiles_h, n = q / p.tiles_h;
+        const int h0 = th * HALO_TH, w0 = tw * HALO_TW;
+        const int s = i % STAGES;
+        mbar_wait(smem_u32(&empty_bar[s]), ((i / STAGES) & 1) ^ 1);
+        const uint32_t bar = smem_u32(&full_bar[s]);
+        mbar_expect_tx(bar, NSPLIT * (HALO_BOX_BYTES + WGH_DY_BYTES));
+        uint8_t* stg = smem + (size_t)s * STAGE;
+        tma_load_4d(smem_u32(stg), &tm_x_hi, bar, 0, h0 - 1, w0 - 1, n);                               // map dims {c, h, w, n}
+        tma_load_4d(smem_u32(stg + NSPLIT * WGH_X_SLOT), &tm_dy_hi, bar, 0, h0, w0, n);
+        if (NSPLIT == 2) {
+          tma_load_4d(smem_u32(stg + WGH_X_SLOT), &tm_x_lo, bar, 0, h0 - 1, w0 - 1, n);
+          tma_load_4d(smem_u32(stg + NSPLIT * WGH_X_SLOT + WGH_DY_BYTES), &tm_dy_lo, bar, 0, h0, w0, n);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // the whole warp walks the issue loop; one elected lane issues (umma_bf16_elect).  Descriptors = base + compile-time constants.
+    for (int i = 0; i < my_tiles; ++i) {
+      const int s = i % STAGES;
+      mbar_wait(smem_u32(&full_bar[s]), (i / STAGES) & 1);
+      tc_fence_after();
+      const uint32_t stg = smem_u32(smem + (size_t)s * STAGE);
+      const uint32_t x_hi = stg, x_lo = stg + WGH_X_SLOT;
+      const uint32_t d_hi = stg + NSPLIT * WGH_X_SLOT, d_lo = d_hi + WGH_DY_BYTES;
+#pragma unroll
+      for (int pr = 0; pr < WGH_PAIRS; ++pr) {
+        constexpr int dummy = 0; (void)dummy;
+        const int oa = wgh_off(wgh_tap_a(pr)), ob = wgh_off(wgh_tap_b(pr));
+        const uint64_t a_hi0 = make_mnmajor_sw128_desc(x_hi + oa * 128, (uint32_t)(ob - oa) * 128u, HALO_BH * 128);
+        const uint64_t a_lo0 = make_mnmajor_sw128_desc(x_lo + oa * 128, (uint32_t)(ob - oa) * 128u, HALO_BH * 128);
+        const uint64_t b_hi0 = make_mnmajor_sw128_desc(d_hi, 1024, 1024);
+        const uint64_t b_lo0 = make_mnmajor_sw128_desc(d_lo, 1024, 1024);
+        const uint32_t acc = tmem_base + (uint32_t)(pr * 64);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {                    // 16 pixels: columns 2kk, 2kk + 1 of the tile
+          const uint64_t a_adv = (uint64_t)((2 * kk * HALO_BH * 128) >> 4);
+          const uint64_t b_adv = (uint64_t)((kk * 16 * 128) >> 4);
+          if (NPROD == 3) {
+            umma_bf16_elect(acc, a_hi0 + a_adv, b_lo0 + b_adv, IDESC, (i | kk) != 0);
+            umma_bf16_elect(acc, a_lo0 + a_adv, b_hi0 + b_adv, IDESC, 1);
+            umma_bf16_elect(acc, a_hi0 + a_adv, b_hi0 + b_adv, IDESC, 1);
+          } else {
+            umma_bf16_elect(acc, a_hi0 + a_adv, b_hi0 + b_adv, IDESC, (i | kk) != 0);
+          }
+        }
+      }
+      umma_commit_elect(smem_u32(&empty_bar[s]));
+    }
+    umma_commit_elect(smem_u32(&done_bar));
+  } else if (my_tiles > 0) {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;                      // accumulator row = (tap of the pair: m / 64, input channel m % 64)
+    const int ci = m & 63;
+    mbar_wait(smem_u32(&done_bar), 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int pr = 0; pr < WGH_PAIRS; ++pr) {
+      const int tap = (m < 64) ? wgh_tap_a(pr) : wgh_tap_b(pr);
+      const bool live = pr < WGH_PAIRS - 1 || m < 64;      // the last pair holds tap 8 twice
+      float* dst = p.dwp + (size_t)tap * 64 * 64 + ci;     // [tap][co][ci]: + co * 64
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(pr * 64 + c * 32), v);
+        if (live) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(dst + (size_t)(c * 32 + j) * 64, __uint_as_float(v[j]));    // result unused: RED
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(NCOLS));
+  }
+}
+
 // dwp[tap][co][ci] -> dw[co][ci][r][s]
 __global__ void unpack_wgrad_tc_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Cout, int Cin, int taps) {
+  pdl_prologue();
   const int64_t total = (int64_t)Cout * Cin * taps;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int tap = (int)(i % taps); int64_t q = i / taps;
@@ -731,6 +1233,7 @@ __global__ void unpack_wgrad_tc_kernel(const float* __restrict__ dwp, float* __r
 // [taps][Cout][Cin] accumulator in one scratch array and converts a whole gradient bucket (a residual layer) at once.
 // kind 1 = stem: dW'[co][192] (k = (r*7+s)*3 + c) -> conv1.weight gradient [64][3][7][7].
 __global__ void unpack_wgrad_batched_kernel(const float* __restrict__ dwp_base, float* __restrict__ grads_base, TcUnpackTable t) {
+  pdl_prologue();
   const TcUnpackEntry en = t.e[blockIdx.y];
   const float* __restrict__ dwp = dwp_base + en.src_off;
   float* __restrict__ dw = grads_base + en.dst_off;
@@ -753,6 +1256,7 @@ __global__ void unpack_wgrad_batched_kernel(const float* __restrict__ dwp_base, 
 // x fp32 -> hi = bf16(x), lo = bf16(x - hi)      (n multiple of 4)
 __global__ void split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                   int64_t n4, int want_lo) {
+  pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
     __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z), h3 = __float2bfloat16_rn(v.w);
@@ -772,6 +1276,7 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __
 //                             dgrad: B[ci][(r'*k+s')*Cout + co]  with (r,s) = (k-1-r', k-1-s')
 __global__ void pack_weights_tc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                        int Cout, int Cin, int k, int dgrad, int want_lo) {
+  pdl_prologue();
   const int64_t total = (int64_t)Cout * Cin * k * k;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int co, ci, r, s;
@@ -796,6 +1301,7 @@ __global__ void pack_weights_tc_kernel(const float* __restrict__ w, __nv_bfloat1
 // The data gradient of a stride-2 convolution is then an ordinary stride-1 convolution over these planes.
 __global__ void upsample_zero_split_kernel(const float* __restrict__ dy, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                            int N, int Ho, int Wo, int C, int want_lo) {
+  pdl_prologue();
   const int q = C >> 2;
   const int64_t total = (int64_t)N * Ho * Wo * q;
   const uint2 z = make_uint2(0u, 0u);
@@ -830,6 +1336,7 @@ constexpr int STEM_COLS = 2 * STEM_TW + 5;
 __global__ void __launch_bounds__(256)
 stem_patch_split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                         int N, int H, int W, int H1, int W1, int want_lo) {
+  pdl_prologue();
   __shared__ float tile[3 * 7 * (STEM_COLS + 1) + 4];
   __shared__ int koff[192];          // k -> offset of (c, r, s) inside `tile` (the + 2*px part is added per pixel); -1 = zero padding
   const int wt = blockIdx.x, ho = blockIdx.y, n = blockIdx.z;
@@ -877,6 +1384,7 @@ stem_patch_split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__
 
 // conv1.weight [64][3][7][7] fp32 -> B[co][k] bf16 hi/lo with k = (r*7+s)*3 + c, zero for k in [147,192)
 __global__ void stem_pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int want_lo) {
+  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 64 * 192) return;
   int k = i % 192, co = i / 192;
@@ -889,6 +1397,7 @@ __global__ void stem_pack_weights_kernel(const float* __restrict__ w, __nv_bfloa
 
 // dW'[co][192] -> conv1.weight gradient [64][3][7][7]
 __global__ void stem_unpack_wgrad_kernel(const float* __restrict__ dwk, float* __restrict__ dw) {
+  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 64 * 147) return;
   int rs = i % 49, c = (i / 49) % 3, co = i / 147;
@@ -903,6 +1412,7 @@ __global__ void stem_unpack_wgrad_kernel(const float* __restrict__ dwk, float* _
 // or NCCL is caught without any host-side version bookkeeping, and an unchanged array costs three tiny launches.
 __global__ void __launch_bounds__(256)
 param_fingerprint_kernel(const uint32_t* __restrict__ w, int64_t n, unsigned long long* __restrict__ fp) {
+  pdl_prologue();
   unsigned long long s1 = 0, s2 = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const unsigned long long v = __ldg(w + i);
@@ -918,6 +1428,7 @@ param_fingerprint_kernel(const uint32_t* __restrict__ w, int64_t n, unsigned lon
 __global__ void __launch_bounds__(256)
 pack_all_kernel(const float* __restrict__ params, char* __restrict__ cache, TcPackTable t, const unsigned long long* __restrict__ fp_new,
                 const unsigned long long* __restrict__ fp_old, int force, int want_lo) {
+  pdl_prologue();
   if (!force && fp_new[0] == fp_old[0] && fp_new[1] == fp_old[1]) return;
   const TcPackEntry en = t.e[blockIdx.y];
   const float* __restrict__ w = params + en.w_off;
@@ -956,6 +1467,7 @@ pack_all_kernel(const float* __restrict__ params, char* __restrict__ cache, TcPa
 }
 
 __global__ void commit_fingerprint_kernel(unsigned long long* fp_new, unsigned long long* fp_old) {
+  pdl_prologue();
   if (threadIdx.x < 2) { fp_old[threadIdx.x] = fp_new[threadIdx.x]; fp_new[threadIdx.x] = 0ull; }
 }
 
@@ -1020,6 +1532,33 @@ static int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, i
   g_maps[key] = *m;
   return 0;
 }
+// Halo boxes of conv64_halo_kernel: the same NHWC planes with H and W swapped in the map, {c, h, w, n}, so that a box lands in
+// shared memory as [w][h][64 c] (8 consecutive rows of a pixel column form one UMMA core-matrix group).
+static int make_act_map_hw(CUtensorMap* m, const void* base, int N, int H, int W, int C, int box_h, int box_w) {
+  const MapKey key = {base, C, H, W, N, TC_BLOCK_K, box_h, box_w, -2};
+  {
+    std::lock_guard<std::mutex> lk(g_maps_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *m = it->second; return 0; }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)"); return DDN_EUNSUPPORTED; }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)H, (cuuint64_t)W, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)W * C * 2, (cuuint64_t)C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)box_h, (cuuint32_t)box_w, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(halo activations) failed: %d", (int)r); return DDN_EINVAL; }
+  std::lock_guard<std::mutex> lk(g_maps_mu);
+  if (g_maps.size() > 8192) g_maps.clear();
+  g_maps[key] = *m;
+  return 0;
+}
+static int make_act_map_halo(CUtensorMap* m, const void* base, int N, int H, int W, int C) {
+  return make_act_map_hw(m, base, N, H, W, C, HALO_BH, HALO_BW);
+}
 static int make_weight_map(CUtensorMap* m, const void* base, int rows, int K, int box_rows) {
   const MapKey key = {base, K, rows, 0, 0, TC_BLOCK_K, box_rows, 0, -1};
   {
@@ -1041,6 +1580,12 @@ static int make_weight_map(CUtensorMap* m, const void* base, int rows, int K, in
   if (g_maps.size() > 8192) g_maps.clear();
   g_maps[key] = *m;
   return 0;
+}
+
+static bool tc_halo_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DDN_TC_HALO"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
 }
 
 template <int BN, int T, int NPROD>
@@ -1071,6 +1616,36 @@ int tc_wgrad_planes(TcPlanes x, TcPlanes dy, float* dw, int N, int H, int W, int
   const int taps = k * k;
   const int Ho = H / stride, Wo = W / stride;
   if (dw) DDN_TRY(launch_fill_zero(dwp, sizeof(float) * (size_t)taps * Cout * Cin, st));
+  if (tc_halo_enabled() && k == 3 && Cin == 64 && Cout == 64 && stride == 1 && dil == 1 && H % HALO_TH == 0 && W % HALO_TW == 0) {
+    // layer1: one halo tile of X + one tile of dY per 8x16 pixels, two taps stacked per MMA (wgrad64_halo_kernel)
+    TcWgradHaloParams hp;
+    hp.dwp = dwp; hp.N = N; hp.H = H; hp.W = W; hp.tiles_h = H / HALO_TH; hp.tiles_w = W / HALO_TW; hp.n_tiles = N * hp.tiles_h * hp.tiles_w;
+    CUtensorMap mx_hi, mx_lo, md_hi, md_lo;
+    DDN_TRY(make_act_map_halo(&mx_hi, x.hi, N, H, W, 64));
+    DDN_TRY(make_act_map_halo(&mx_lo, want_lo ? x.lo : x.hi, N, H, W, 64));
+    DDN_TRY(make_act_map_hw(&md_hi, dy.hi, N, H, W, 64, HALO_TH, HALO_TW));
+    DDN_TRY(make_act_map_hw(&md_lo, want_lo ? dy.lo : dy.hi, N, H, W, 64, HALO_TH, HALO_TW));
+    const int nsplit = want_lo ? 2 : 1;
+    const size_t smem = (size_t)2 * nsplit * (WGH_X_SLOT + WGH_DY_BYTES) + 1024;
+    const int grid = std::min(hp.n_tiles, num_sms());
+    {
+      ProfScope ps(PROF_CONV_WGRAD_TC, 2.0 * N * H * W * 64.0 * 9 * 64, st);
+      if (want_lo) {
+        static bool configured = false;
+        if (!configured) { DDN_CUDA(cudaFuncSetAttribute(wgrad64_halo_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
+        DDN_LAUNCH((wgrad64_halo_kernel<3>), grid, TC_THREADS, smem, st, mx_hi, mx_lo, md_hi, md_lo, hp);
+      } else {
+        static bool configured = false;
+        if (!configured) { DDN_CUDA(cudaFuncSetAttribute(wgrad64_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
+        DDN_LAUNCH((wgrad64_halo_kernel<1>), grid, TC_THREADS, smem, st, mx_hi, mx_lo, md_hi, md_lo, hp);
+      }
+    }
+    if (dw) {
+      int blocks = (int)std::min<int64_t>(ceil_div((int64_t)taps * Cout * Cin, 256), 4096);
+      DDN_LAUNCH(unpack_wgrad_tc_kernel, blocks, 256, 0, st, dwp, dw, Cout, Cin, taps);
+    }
+    return 0;
+  }
   const int bn = Cin % 128 == 0 ? 128 : 64;
   CUtensorMap m_dy_hi, m_dy_lo, m_x_hi, m_x_lo;
   DDN_TRY(make_act_map(&m_dy_hi, dy.hi, N, Ho, Wo, Cout));
@@ -1200,14 +1775,36 @@ static int launch_conv_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, cons
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
+  int n_attr = 0;
   if (PAIR) {
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+    attr[n_attr].val.clusterDim.x = 2; attr[n_attr].val.clusterDim.y = 1; attr[n_attr].val.clusterDim.z = 1;
+    ++n_attr;
   }
+  if (pdl_enabled()) {
+    attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+    ++n_attr;
+  }
+  cfg.attrs = attr; cfg.numAttrs = n_attr;
   DDN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, NPROD, PAIR>, a_hi, a_lo, b_hi, b_lo, bt_hi, bt_lo, p));
   g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+template <int NPROD>
+static int launch_conv64_halo(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                              const TcHaloParams& p, cudaStream_t st) {
+  constexpr int NSPLIT = NPROD == 3 ? 2 : 1;
+  const size_t smem = (size_t)NSPLIT * HALO_B_PLANE + (size_t)HALO_SLOTS * HALO_SLOT + 1024;
+  static bool configured = false;
+  if (!configured) {
+    DDN_CUDA(cudaFuncSetAttribute(conv64_halo_kernel<NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int grid = std::min(p.n_tiles, num_sms());
+  DDN_LAUNCH((conv64_halo_kernel<NPROD>), grid, TC_THREADS, smem, st, a_hi, a_lo, b_hi, b_lo, p);
   return 0;
 }
 
@@ -1218,9 +1815,11 @@ static int launch_conv_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, cons
 //   wpk != nullptr: weights are already packed [gout][k*k*gin] bf16 hi/lo; else they are packed from w_oihw into `wws`.
 //   stats (forward only): per-channel sum / sum of squares of the output go to stats->a, and the kernel's last CTA writes
 //              the BatchNorm statistics described by *stats; groups = BatchNorm groups in the batch.
+//   bst (data gradient only): the gradient written to `out` is the dY of a BatchNorm whose column sums (sum g, sum g*xhat,
+//              g = dY * relu mask) are accumulated by the epilogue; the last CTA finalizes them like bn_colsum_kernel<1>.
 int tc_conv_planes(TcPlanes in, const float* w_oihw, const TcPlanes* wpk, float* out, const float* addend, const BnFwdFinal* stats,
                    int N, int H, int W, int Cin, int Cout, int k, int stride, int dil, int dgrad, int precision,
-                   void* wws, size_t wws_bytes, cudaStream_t st, const TcFoldedEpilogue* ep) {
+                   void* wws, size_t wws_bytes, cudaStream_t st, const TcFoldedEpilogue* ep, const TcBwdStats* bst) {
   DDN_CHECK_ARG(stride == 1 || !dgrad, "the strided data gradient goes through zero-inserted planes (stride 1 here)");
   const int Ho = H / stride, Wo = W / stride;
   const double fl = 2.0 * N * Ho * Wo * (double)Cout * k * k * Cin;
@@ -1239,6 +1838,27 @@ int tc_conv_planes(TcPlanes in, const float* w_oihw, const TcPlanes* wpk, float*
     int wblocks = (int)std::min<int64_t>(ceil_div((int64_t)wel, 256), 4096);
     DDN_LAUNCH(pack_weights_tc_kernel, wblocks, 256, 0, st, w_oihw, ph, pl, Cout, Cin, k, dgrad, want_lo);
     b_hi = ph; b_lo = pl;
+  }
+  if (tc_halo_enabled() && k == 3 && gin == 64 && gout == 64 && stride == 1 && dil == 1 && !ep && !bst && Ho % HALO_TH == 0 && Wo % HALO_TW == 0) {
+    // 64 -> 64 channels (layer1): resident weights + one halo tile per 8x16 output pixels (conv64_halo_kernel)
+    TcHaloParams hp;
+    memset(&hp, 0, sizeof(hp));
+    DDN_CHECK_ARG(out != nullptr, "conv output pointer is null");
+    hp.out = out; hp.addend = addend; hp.N = N; hp.H = Ho; hp.W = Wo;
+    hp.tiles_h = Ho / HALO_TH; hp.tiles_w = Wo / HALO_TW; hp.n_tiles = N * hp.tiles_h * hp.tiles_w;
+    hp.imgs_per_group = N;
+    if (stats) {
+      DDN_CHECK_ARG(!dgrad && stats->G >= 1 && stats->G <= BN_MAX_GROUPS && N % stats->G == 0 && stats->C == 64, "bad BatchNorm statistics request");
+      hp.fin = *stats;
+      hp.imgs_per_group = N / stats->G;
+    }
+    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+    DDN_TRY(make_act_map_halo(&ma_hi, in.hi, N, H, W, 64));
+    DDN_TRY(make_act_map_halo(&ma_lo, want_lo ? in.lo : in.hi, N, H, W, 64));
+    DDN_TRY(make_weight_map(&mb_hi, b_hi, 64, 9 * 64, 64));
+    DDN_TRY(make_weight_map(&mb_lo, want_lo ? b_lo : b_hi, 64, 9 * 64, 64));
+    ProfScope ps(dgrad ? PROF_CONV_DGRAD_TC : PROF_CONV_FWD_TC, fl, st);
+    return want_lo ? launch_conv64_halo<3>(ma_hi, ma_lo, mb_hi, mb_lo, hp, st) : launch_conv64_halo<1>(ma_hi, ma_lo, mb_hi, mb_lo, hp, st);
   }
   const bool pair = tc_pair_enabled() && gout % 256 == 0;
   const int block_n = pair ? 256 : gout % 128 == 0 ? 128 : 64;
@@ -1267,6 +1887,13 @@ int tc_conv_planes(TcPlanes in, const float* w_oihw, const TcPlanes* wpk, float*
     p.fin = *stats;
     p.imgs_per_group = N / stats->G;
   }
+  if (bst) {
+    DDN_CHECK_ARG(dgrad && !ep && !stats && bst->raw && bst->mean && bst->invstd && bst->fin.a.acc && bst->fin.G >= 1 &&
+                  bst->fin.G <= BN_MAX_GROUPS && N % bst->fin.G == 0 && bst->fin.C == gout && (bst->y_hi || !bst->relu || (bst->gamma && bst->beta)),
+                  "bad BatchNorm backward-statistics request");
+    p.bst = *bst;
+    p.imgs_per_group = N / bst->fin.G;
+  }
   if (ep) {
     DDN_CHECK_ARG(!dgrad && !stats && ep->scale && ep->shift && (out || ep->out_hi), "folded epilogue: forward only, needs scale/shift and an output");
     p.ep_scale = ep->scale; p.ep_shift = ep->shift; p.ep_relu = ep->relu; p.out_hi = ep->out_hi; p.out_lo = want_lo ? ep->out_lo : nullptr;
@@ -1294,10 +1921,11 @@ int tc_conv_planes(TcPlanes in, const float* w_oihw, const TcPlanes* wpk, float*
 
 // data gradient of a stride-2 conv: zero-insert dY [N,H/2,W/2,Cout] into `up` planes [N,H,W,Cout], then a stride-1 dgrad
 int tc_dgrad_strided(const float* dy_f32, TcPlanes up, const float* w_oihw, const TcPlanes* w_packed, float* dx, const float* addend,
-                     int N, int H, int W, int Cin, int Cout, int k, int precision, void* wws, size_t wws_bytes, cudaStream_t st) {
+                     int N, int H, int W, int Cin, int Cout, int k, int precision, void* wws, size_t wws_bytes, cudaStream_t st,
+                     const TcBwdStats* bst) {
   DDN_TRY(tc_upsample_zero_split(dy_f32, const_cast<__nv_bfloat16*>(up.hi), const_cast<__nv_bfloat16*>(up.lo), N, H / 2, W / 2, Cout,
                                  precision, st));
-  return tc_conv_planes(up, w_oihw, w_packed, dx, addend, nullptr, N, H, W, Cin, Cout, k, 1, 1, 1, precision, wws, wws_bytes, st);
+  return tc_conv_planes(up, w_oihw, w_packed, dx, addend, nullptr, N, H, W, Cin, Cout, k, 1, 1, 1, precision, wws, wws_bytes, st, nullptr, bst);
 }
 
 // ---- stem (conv1 7x7/2, Cin = 3) as a K = 192 GEMM over patch planes

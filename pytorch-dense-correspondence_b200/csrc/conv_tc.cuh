@@ -13,6 +13,18 @@ struct TcPlanes { const __nv_bfloat16* hi; const __nv_bfloat16* lo; };   // x ~=
 struct TcFoldedEpilogue { const float* scale; const float* shift; int relu; __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; };
 bool tc_folded_epilogue_supported();
 
+// Data-gradient epilogue that also produces the column sums of the BatchNorm backward consuming the gradient it writes:
+// out = dY of y = relu?(bn(raw) [+ residual]); g = out * (y > 0) with the mask taken from the bf16 hi plane of y (`y_hi`, blocks
+// with a residual) or recomputed from raw (relu, no residual); (sum g, sum g * xhat) per channel and BatchNorm group go through
+// fin.a, and the kernel's last CTA writes fin.sums / dgamma / dbeta -- exactly what bn_colsum_kernel<1> would, one pass earlier.
+struct TcBwdStats {
+  const float* raw; const __nv_bfloat16* y_hi;
+  const float* mean; const float* invstd;      // [G][C]
+  const float* gamma; const float* beta;       // [C]
+  int relu;
+  BnBwdFinal fin;
+};
+
 bool tc_available();
 // forward / weight gradient: 3x3 (pad == dil) or 1x1 (pad 0), Cin and Cout multiples of 64, stride 1 (any dil) or 2 (dil 1)
 bool tc_conv_supported(int Cin, int Cout, int k, int stride, int pad, int dil, int H, int W);
@@ -25,11 +37,12 @@ int tc_split(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t n, in
 // CTA writes the BatchNorm statistics (bn_stats.cuh); stats->G BatchNorm groups of N / G images each.
 int tc_conv_planes(TcPlanes in, const float* w_oihw, const TcPlanes* w_packed, float* out, const float* addend, const BnFwdFinal* stats,
                    int N, int H, int W, int Cin, int Cout, int k, int stride, int dil, int dgrad, int precision,
-                   void* wws, size_t wws_bytes, cudaStream_t st, const TcFoldedEpilogue* ep = nullptr);
+                   void* wws, size_t wws_bytes, cudaStream_t st, const TcFoldedEpilogue* ep = nullptr, const TcBwdStats* bst = nullptr);
 int tc_pack_weights(const float* w_oihw, __nv_bfloat16* hi, __nv_bfloat16* lo, int Cout, int Cin, int k, int dgrad, int precision,
                     cudaStream_t st);
 int tc_dgrad_strided(const float* dy_f32, TcPlanes up, const float* w_oihw, const TcPlanes* w_packed, float* dx, const float* addend,
-                     int N, int H, int W, int Cin, int Cout, int k, int precision, void* wws, size_t wws_bytes, cudaStream_t st);
+                     int N, int H, int W, int Cin, int Cout, int k, int precision, void* wws, size_t wws_bytes, cudaStream_t st,
+                     const TcBwdStats* bst = nullptr);
 // dw != nullptr: immediate (dwp = scratch, zero-filled and converted here); dw == nullptr: accumulate into the caller's pre-zeroed
 // dwp [taps][Cout][Cin] and convert later with tc_unpack_wgrads (one launch for a whole gradient bucket)
 int tc_wgrad_planes(TcPlanes x, TcPlanes dy, float* dw, int N, int H, int W, int Cin, int Cout, int k, int stride, int dil,

@@ -24,6 +24,12 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DDN_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -236,7 +242,7 @@ static int make_plan(Plan* p, int B, int H, int W, int D, int mode, int precisio
   max_w = std::max(max_w, (size_t)7 * 7 * 4 * 64);
   p->wpack = f32((int64_t)max_w); p->wpack2 = f32((int64_t)max_w); p->dwp = f32((int64_t)max_w);
   p->acc = alloc(bn_accum_bytes(512));
-  p->sums = f32(2 * G * 512);
+  p->sums = f32(3 * 2 * G * 512);     // [0]: standalone column-sum pass, [1], [2]: sums produced by a data-gradient epilogue
   p->scratch_elems = (size_t)max_act;
   for (int i = 0; i < 4; ++i) p->scratch[i] = f32((int64_t)max_act);
   p->grad_p = planes(max_act);
@@ -478,7 +484,7 @@ static int net_forward(const Ctx& c, const float* x, float* y, float* low_nhwc) 
 // (+ addend) when dx != nullptr.  Tensor-core convs take the saved bf16 planes of their input and the planes of dY
 // (p.grad_p, written by the BN backward that precedes this call); the fp32 SIMT convs take the fp32 tensors.
 static int conv_backward(const Ctx& c, const ConvSpec& cs, const float* in, const PlaneBufs& in_p, const float* dy, float* dx,
-                         const float* addend, int N, int Hin, int Win, int Hout, int Wout, int cin_eff) {
+                         const float* addend, int N, int Hin, int Win, int Hout, int Wout, int cin_eff, const TcBwdStats* bst = nullptr) {
   const Plan& p = *c.p;
   const float* w = c.params + cs.w_off;
   float* dw = c.grads + cs.w_off;
@@ -490,13 +496,14 @@ static int conv_backward(const Ctx& c, const ConvSpec& cs, const float* in, cons
       TcPlanes wpk_s; const TcPlanes* wpk = cached_pack(c, cs, 1, &wpk_s);
       if (cs.stride == 2)   // zero-insert the fp32 dY into the (now free) gradient planes, then an ordinary stride-1 dgrad
         DDN_TRY(tc_dgrad_strided(dy, c.planes(p.grad_p), w, wpk, dx, addend, N, Hin, Win, cs.cin, cs.cout, cs.k, p.precision,
-                                 c.ws + p.wws, tc_weight_ws_bytes(), c.st));
+                                 c.ws + p.wws, tc_weight_ws_bytes(), c.st, bst));
       else
         DDN_TRY(tc_conv_planes(c.planes(p.grad_p), w, wpk, dx, addend, nullptr, N, Hin, Win, cs.cin, cs.cout, cs.k, 1, cs.dil, 1,
-                               p.precision, c.ws + p.wws, tc_weight_ws_bytes(), c.st));
+                               p.precision, c.ws + p.wws, tc_weight_ws_bytes(), c.st, nullptr, bst));
     }
     return 0;
   }
+  DDN_CHECK_ARG(bst == nullptr, "backward statistics can only ride on a tensor-core data gradient");
   ConvGeom g;
   DDN_TRY(conv_geom_init(&g, N, Hin, Win, cin_eff, Hout, Wout, cs.cout, cs.k, cs.k, cs.stride, 1, cs.pad, cs.dil));
   size_t wbytes = sizeof(float) * (size_t)cs.k * cs.k * cin_eff * cs.cout;
@@ -518,15 +525,18 @@ static int conv_backward(const Ctx& c, const ConvSpec& cs, const float* in, cons
 
 // BN backward of `bs` (output y = relu?(bn(raw) + res)) whose dx feeds conv `cs`'s backward: planes for a tensor-core conv,
 // fp32 for a SIMT conv.  mask: the bf16 hi plane of y / the fp32 y / recomputed from raw (no residual) -- see BnBwdArgs.
+// fused_slot > 0: the column sums were produced by the data-gradient epilogue that wrote `dy` (bwd_stats_for) -- skip that pass.
 static int bn_backward_for(const Ctx& c, const BnSpec& bs, const ConvBufs& cb, const float* dy, const float* y_f32,
-                           const __nv_bfloat16* y_hi, int relu, float* g_out, const ConvSpec& cs, int Hin, int Win, float* dx_f32, int64_t M) {
+                           const __nv_bfloat16* y_hi, int relu, float* g_out, const ConvSpec& cs, int Hin, int Win, float* dx_f32, int64_t M,
+                           int fused_slot = 0) {
   BnBwdArgs a;
   memset(&a, 0, sizeof(a));
   a.dy = dy; a.x = c.f(cb.raw); a.mean = c.mean(cb.stats); a.invstd = c.invstd(cb.stats, bs.C);
   a.gamma = c.params + bs.g_off; a.beta = c.params + bs.b_off;
   a.y = y_f32; a.y_hi = y_hi; a.g_out = g_out;
   a.dgamma = c.grads + bs.g_off; a.dbeta = c.grads + bs.b_off;
-  a.acc = c.accum(); a.sums = c.f(c.p->sums);
+  a.acc = c.accum(); a.sums = c.f(c.p->sums) + (size_t)fused_slot * 2 * c.G * 512;
+  a.sums_ready = fused_slot > 0;
   a.M = M; a.C = bs.C; a.relu = relu; a.training = c.training() ? 1 : 0; a.G = c.G;
   if (conv_on_tc(c, cs, Hin, Win)) {
     a.dx = cs.stride == 2 ? dx_f32 : nullptr;      // the strided data gradient re-reads dY in fp32 (zero insertion)
@@ -536,6 +546,24 @@ static int bn_backward_for(const Ctx& c, const BnSpec& bs, const ConvBufs& cb, c
     a.dx = dx_f32;
   }
   return launch_bn_backward(a, c.st);
+}
+
+// Column sums of BatchNorm `bs` (y = relu(bn(raw) [+ residual])) computed by the epilogue of the tensor-core data gradient that
+// produces its dY (conv_tc.cuh TcBwdStats) instead of a separate pass over dY and raw.  Layers narrower than
+// DDN_FUSE_BWD_STATS_MINC channels keep the separate pass: their data gradients are epilogue-bound already.
+static int fuse_bwd_stats_min_c() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DDN_FUSE_BWD_STATS_MINC"); v = e ? atoi(e) : 128; if (v < 0) v = 0; }
+  return v;
+}
+static bool bwd_stats_for(const Ctx& c, const BnSpec& bs, const ConvBufs& cb, const __nv_bfloat16* y_hi, int slot, TcBwdStats* out) {
+  if (!c.p->tc || bs.C < fuse_bwd_stats_min_c()) return false;
+  memset(out, 0, sizeof(*out));
+  out->raw = c.f(cb.raw); out->y_hi = y_hi; out->mean = c.mean(cb.stats); out->invstd = c.invstd(cb.stats, bs.C);
+  out->gamma = c.params + bs.g_off; out->beta = c.params + bs.b_off; out->relu = 1;
+  out->fin.a = c.accum(); out->fin.sums = c.f(c.p->sums) + (size_t)slot * 2 * c.G * 512;
+  out->fin.dgamma = c.grads + bs.g_off; out->fin.dbeta = c.grads + bs.b_off; out->fin.G = c.G; out->fin.C = bs.C;
+  return true;
 }
 
 // gradient buckets, in the order the backward completes them (ddn_grad_bucket_fn): [first block of the layer .. next bucket)
@@ -571,6 +599,7 @@ static int net_backward(const Ctx& c, const float* dy, const float* dlow_nhwc, d
     ++bucket_id; bucket_end = begin;
     return 0;
   };
+  bool b2_fused = false;    // the column sums of this block's bn2 came out of the next block's conv1 data gradient (slot 2)
   for (int i = (int)s.blocks.size() - 1; i >= 0; --i) {
     const BlockSpec& b = s.blocks[i]; const BlockBufs& bb = p.blk[i];
     const float* xin = p.tc ? nullptr : (i == 0 ? c.f(p.pool_out) : c.f(p.blk[i - 1].out));
@@ -579,16 +608,23 @@ static int net_backward(const Ctx& c, const float* dy, const float* dlow_nhwc, d
     int t1 = (cur + 1) & 3, t2 = (cur + 2) & 3, t3 = (cur + 3) & 3;
     // out = relu(bn2(raw2) + residual):  g = dOut*(out>0) -> S[t2];  d raw2 -> planes (tensor core) or S[t1] (fp32)
     DDN_TRY(bn_backward_for(c, b.b2, bb.c2, S[cur], p.tc ? nullptr : c.f(bb.out), p.tc ? c.h(bb.out_p.hi) : nullptr, 1, S[t2], b.c2,
-                            bb.c2.Hin, bb.c2.Win, S[t1], M1));
-    // conv2: dW, d act1 -> S[t3]
+                            bb.c2.Hin, bb.c2.Win, S[t1], M1, b2_fused ? 2 : 0));
+    // conv2: dW, d act1 -> S[t3] (+ the column sums of bn1's backward, in the same epilogue)
+    TcBwdStats st1, st2;
+    const bool b1_fused = conv_on_tc(c, b.c2, bb.c2.Hin, bb.c2.Win) && bwd_stats_for(c, b.b1, bb.c1, nullptr, 1, &st1);
     DDN_TRY(conv_backward(c, b.c2, p.tc ? nullptr : c.f(bb.act1), bb.act1_p, S[t1], S[t3], nullptr, B, bb.c2.Hin, bb.c2.Win, bb.c2.Hout,
-                          bb.c2.Wout, b.c2.cin));
+                          bb.c2.Wout, b.c2.cin, b1_fused ? &st1 : nullptr));
     defer(b.c2, bb.c2.Hin, bb.c2.Win);
+    // conv1's data gradient completes d(block input) = dOut of the previous block: bn2 of that block gets its column sums there
+    b2_fused = i > 0 && conv_on_tc(c, b.c1, bb.c1.Hin, bb.c1.Win) &&
+               bwd_stats_for(c, s.blocks[i - 1].b2, p.blk[i - 1].c2, c.h(p.blk[i - 1].out_p.hi), 2, &st2);
     // act1 = relu(bn1(raw1)), no residual: the mask is recomputed from raw1 in the tensor-core modes
     if (!b.has_ds) {
-      DDN_TRY(bn_backward_for(c, b.b1, bb.c1, S[t3], p.tc ? nullptr : c.f(bb.act1), nullptr, 1, nullptr, b.c1, bb.c1.Hin, bb.c1.Win, S[t1], M1));
+      DDN_TRY(bn_backward_for(c, b.b1, bb.c1, S[t3], p.tc ? nullptr : c.f(bb.act1), nullptr, 1, nullptr, b.c1, bb.c1.Hin, bb.c1.Win, S[t1], M1,
+                              b1_fused ? 1 : 0));
       // dX = dgrad(conv1) + g
-      DDN_TRY(conv_backward(c, b.c1, xin, xin_p, S[t1], S[t3], S[t2], B, bb.c1.Hin, bb.c1.Win, bb.c1.Hout, bb.c1.Wout, b.c1.cin));
+      DDN_TRY(conv_backward(c, b.c1, xin, xin_p, S[t1], S[t3], S[t2], B, bb.c1.Hin, bb.c1.Win, bb.c1.Hout, bb.c1.Wout, b.c1.cin,
+                            b2_fused ? &st2 : nullptr));
       defer(b.c1, bb.c1.Hin, bb.c1.Win);
       cur = t3;
     } else {
@@ -598,8 +634,10 @@ static int net_backward(const Ctx& c, const float* dy, const float* dlow_nhwc, d
       DDN_TRY(conv_backward(c, b.ds, xin, xin_p, S[t1], S[cur], nullptr, B, bb.ds.Hin, bb.ds.Win, bb.ds.Hout, bb.ds.Wout, b.ds.cin));
       defer(b.ds, bb.ds.Hin, bb.ds.Win);
       // main branch: d raw1, then dX = dgrad(conv1) + dX_ds -> S[t2]
-      DDN_TRY(bn_backward_for(c, b.b1, bb.c1, S[t3], p.tc ? nullptr : c.f(bb.act1), nullptr, 1, nullptr, b.c1, bb.c1.Hin, bb.c1.Win, S[t1], M1));
-      DDN_TRY(conv_backward(c, b.c1, xin, xin_p, S[t1], S[t2], S[cur], B, bb.c1.Hin, bb.c1.Win, bb.c1.Hout, bb.c1.Wout, b.c1.cin));
+      DDN_TRY(bn_backward_for(c, b.b1, bb.c1, S[t3], p.tc ? nullptr : c.f(bb.act1), nullptr, 1, nullptr, b.c1, bb.c1.Hin, bb.c1.Win, S[t1], M1,
+                              b1_fused ? 1 : 0));
+      DDN_TRY(conv_backward(c, b.c1, xin, xin_p, S[t1], S[t2], S[cur], B, bb.c1.Hin, bb.c1.Win, bb.c1.Hout, bb.c1.Wout, b.c1.cin,
+                            b2_fused ? &st2 : nullptr));
       defer(b.c1, bb.c1.Hin, bb.c1.Win);
       cur = t2;
       // a block with a downsample branch opens a residual layer: everything from its first parameter up is final now

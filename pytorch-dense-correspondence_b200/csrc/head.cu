@@ -10,6 +10,7 @@ constexpr int FC_MAXD = 32;
 
 // x [N,3,H,W] -> y [N,H,W,4] (4th channel zero) so the stem conv can use float4 gathers
 __global__ void nchw_to_nhwc4_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int64_t HW) {
+  pdl_prologue();
   int64_t total = (int64_t)N * HW;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t n = i / HW, p = i - n * HW;
@@ -38,6 +39,7 @@ __global__ void __launch_bounds__(256)
 fc_forward_kernel(const float* __restrict__ feat, const __nv_bfloat16* __restrict__ feat_hi, const __nv_bfloat16* __restrict__ feat_lo,
                   const float* __restrict__ w, const float* __restrict__ bias,
                   float* __restrict__ low, float* __restrict__ low_t, int64_t Mimg, int N, int C, int D) {
+  pdl_prologue();
   extern __shared__ float ws[];   // [D][C]
   for (int i = threadIdx.x; i < D * C; i += blockDim.x) ws[i] = w[i];
   __syncthreads();
@@ -77,6 +79,7 @@ template <int DM>
 __global__ void __launch_bounds__(256)
 fc_dgrad_kernel(const float* __restrict__ dlow, const float* __restrict__ w, float* __restrict__ dfeat,
                 int64_t Mimg, int N, int C, int D) {
+  pdl_prologue();
   extern __shared__ float ws[];
   for (int i = threadIdx.x; i < D * C; i += blockDim.x) ws[i] = w[i];
   __syncthreads();
@@ -104,6 +107,7 @@ __global__ void __launch_bounds__(256)
 fc_wgrad_kernel(const float* __restrict__ dlow, const float* __restrict__ feat, const __nv_bfloat16* __restrict__ feat_hi,
                 const __nv_bfloat16* __restrict__ feat_lo, float* __restrict__ dw,
                 float* __restrict__ dbias, int64_t Mimg, int N, int C, int D, int pix_per_block) {
+  pdl_prologue();
   const int64_t total = (int64_t)N * Mimg;
   const int64_t p0 = (int64_t)blockIdx.x * pix_per_block;
   const int64_t p1 = min(total, p0 + pix_per_block);
@@ -165,6 +169,7 @@ __device__ __forceinline__ void src_index(float scale, int dst, int in_size, int
 __global__ void __launch_bounds__(256)
 upsample_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int NC, int h, int w, int H, int W,
                     float sh, float sw) {
+  pdl_prologue();
   // thread -> 4 consecutive output columns of one row of one map
   const int Wq = W >> 2;
   const int64_t total = (int64_t)NC * H * Wq;
@@ -192,6 +197,7 @@ upsample_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int NC, 
 __global__ void __launch_bounds__(256)
 upsample_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int NC, int h, int w, int H, int W,
                     float sh, float sw, float inv_sh, float inv_sw) {
+  pdl_prologue();
   const int64_t total = (int64_t)NC * h * w;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int j = (int)(i % w); int64_t t = i / w;
@@ -293,6 +299,7 @@ int launch_upsample_bwd(const float* dy, float* dx, int NC, int h, int w, int H,
 
 // dlow [N, D, Mimg] (+)= dlow_t [N, Mimg, D]: the gradient the fused loss scattered into the NHWC low-resolution map
 __global__ void add_lowres_nhwc_kernel(const float* __restrict__ dlow_t, float* __restrict__ dlow, int64_t Mimg, int N, int D, int accumulate) {
+  pdl_prologue();
   const int64_t total = (int64_t)N * D * Mimg;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t p = i % Mimg; const int64_t t = i / Mimg;

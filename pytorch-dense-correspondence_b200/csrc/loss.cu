@@ -15,6 +15,7 @@ loss_terms_fwd_kernel(const float* __restrict__ pa, const float* __restrict__ pb
                       int64_t sb, int64_t sp, int64_t sc, int64_t P, int D_rt, int W,
                       const __grid_constant__ DevTerms T, double* __restrict__ sums,
                       unsigned long long* __restrict__ counts) {
+  pdl_prologue();
   const int D = D_T > 0 ? D_T : D_rt;
   const int b = blockIdx.y;
   const int t = find_term(T, blockIdx.x);
@@ -91,6 +92,7 @@ loss_terms_bwd_kernel(const float* __restrict__ pa, const float* __restrict__ pb
                       int64_t sb, int64_t sp, int64_t sc, int64_t P, int D_rt, int W,
                       const __grid_constant__ DevTerms T, const float* __restrict__ coef,
                       const float* __restrict__ upstream, float* __restrict__ da, float* __restrict__ db) {
+  pdl_prologue();
   const int D = D_T > 0 ? D_T : D_rt;
   constexpr int DM = D_T > 0 ? D_T : LOSS_MAXD;
   const int b = blockIdx.y;
@@ -186,6 +188,7 @@ loss_terms_bwd_kernel(const float* __restrict__ pa, const float* __restrict__ pb
 __global__ void within_scene_compose_kernel(const double* __restrict__ sums, const unsigned long long* __restrict__ counts,
                                             int B, int n_terms, ddn_within_scene_cfg cfg,
                                             float* __restrict__ five, float* __restrict__ coef) {
+  pdl_prologue();
   // One warp; lane-strided over pairs.  loss_composer.py:107-141.
   double acc[5] = {0, 0, 0, 0, 0};
   for (int b = threadIdx.x; b < B; b += 32) {
@@ -226,6 +229,7 @@ __global__ void within_scene_compose_kernel(const double* __restrict__ sums, con
 }
 
 __global__ void scale_inplace_kernel(float* __restrict__ g, int64_t n, float s) {
+  pdl_prologue();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t n4 = n >> 2;
   for (int64_t k = i; k < n4; k += (int64_t)gridDim.x * blockDim.x) {

@@ -84,6 +84,7 @@ template <int D_T>
 __global__ void __launch_bounds__(LR_THREADS)
 loss_lowres_fwd_kernel(const float* __restrict__ la, const float* __restrict__ lb, int h, int w, int H, int W, int D_rt, float sh, float sw,
                        const __grid_constant__ DevTerms T, double* __restrict__ sums, unsigned long long* __restrict__ counts) {
+  pdl_prologue();
   constexpr int DM = D_T > 0 ? D_T : LOSS_MAXD;
   const int D = D_T > 0 ? D_T : D_rt;
   const int b = blockIdx.y;
@@ -169,6 +170,7 @@ __global__ void __launch_bounds__(LR_THREADS)
 loss_lowres_bwd_kernel(const float* __restrict__ la, const float* __restrict__ lb, int h, int w, int H, int W, int D_rt, float sh, float sw,
                        const __grid_constant__ DevTerms T, const float* __restrict__ coef, const float* __restrict__ upstream,
                        float* __restrict__ dla, float* __restrict__ dlb) {
+  pdl_prologue();
   constexpr int DM = D_T > 0 ? D_T : LOSS_MAXD;
   const int D = D_T > 0 ? D_T : D_rt;
   const int b = blockIdx.y;

@@ -19,6 +19,7 @@ best_match_kernel(const float* __restrict__ res_b, int64_t sp, int64_t sc, int64
                   const float* __restrict__ queries, int Q, int pixels_per_block,
                   unsigned long long* __restrict__ best, float* __restrict__ norm_diffs,
                   const float* __restrict__ mask, unsigned long long* __restrict__ best_masked) {
+  pdl_prologue();
   const int q = blockIdx.y;
   __shared__ float qd[MATCH_MAXD];
   if (threadIdx.x < D) qd[threadIdx.x] = queries[(int64_t)q * D + threadIdx.x];
@@ -70,6 +71,7 @@ best_match_kernel(const float* __restrict__ res_b, int64_t sp, int64_t sc, int64
 
 __global__ void best_match_finish_kernel(const unsigned long long* __restrict__ best, int Q, int W,
                                          int64_t* __restrict__ uv, float* __restrict__ diff, int is_distance) {
+  pdl_prologue();
   int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= Q) return;
   unsigned long long k = best[q];

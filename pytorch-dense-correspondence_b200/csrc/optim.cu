@@ -11,6 +11,7 @@ __global__ void __launch_bounds__(256)
 adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n4,
                  int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, float bc1, float bc2_sqrt,
                  float grad_scale) {
+  pdl_prologue();
   const float step_size = lr / bc1;
   auto upd = [&](float& pv, float gv, float& mv, float& vv) {
     gv = fmaf(weight_decay, pv, gv * grad_scale);

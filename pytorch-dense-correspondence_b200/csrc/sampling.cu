@@ -17,6 +17,7 @@ constexpr int SAMP_PER_BLOCK = 1024;     // pixels per block in the compaction p
 
 __global__ void __launch_bounds__(SAMP_THREADS)
 mask_count_kernel(const float* __restrict__ mask, int64_t P, int* __restrict__ block_counts) {
+  pdl_prologue();
   const int64_t base = (int64_t)blockIdx.x * SAMP_PER_BLOCK;
   int c = 0;
 #pragma unroll
@@ -38,6 +39,7 @@ mask_count_kernel(const float* __restrict__ mask, int64_t P, int* __restrict__ b
 // exclusive scan of up to 8192 block counts by one block; total -> counts[nblk]
 __global__ void __launch_bounds__(1024)
 mask_scan_kernel(int* __restrict__ counts, int nblk) {
+  pdl_prologue();
   __shared__ int s[1024];
   __shared__ int carry;
   if (threadIdx.x == 0) carry = 0;
@@ -65,6 +67,7 @@ mask_scan_kernel(int* __restrict__ counts, int nblk) {
 // ascending list of the nonzero pixels (== torch.nonzero order)
 __global__ void __launch_bounds__(SAMP_THREADS)
 mask_compact_kernel(const float* __restrict__ mask, int64_t P, const int* __restrict__ block_offsets, int* __restrict__ nz) {
+  pdl_prologue();
   const int64_t base = (int64_t)blockIdx.x * SAMP_PER_BLOCK;
   __shared__ int warp_tot[SAMP_PER_BLOCK / 32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -93,6 +96,7 @@ __global__ void __launch_bounds__(SAMP_THREADS)
 sample_non_matches_kernel(const int* __restrict__ nz, const int* __restrict__ total, const float* __restrict__ rand_u,
                           const float* __restrict__ rand_v, int64_t n, int H, int W, const int64_t* __restrict__ matches_a,
                           int64_t k, int64_t* __restrict__ out_a, int64_t* __restrict__ out_b) {
+  pdl_prologue();
   const int L = total ? total[0] : 0;
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
     int64_t b;
@@ -171,6 +175,7 @@ __global__ void __launch_bounds__(SAMP_THREADS)
 reproject_kernel(const float* __restrict__ depth_a, const float* __restrict__ depth_b, const int64_t* __restrict__ cand, int64_t n,
                  int H, int W, const __grid_constant__ ReprojMats m, float* __restrict__ flag, int64_t* __restrict__ b_flat,
                  float* __restrict__ u2o, float* __restrict__ v2o) {
+  pdl_prologue();
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
     const int64_t ia = cand[j];
     float ok = 0.f; int64_t bf = 0; float u2 = 0.f, v2 = 0.f;
@@ -205,6 +210,7 @@ reproject_gather_kernel(const int* __restrict__ nz, const int* __restrict__ tota
                         const int64_t* __restrict__ b_flat, const float* __restrict__ u2, const float* __restrict__ v2,
                         int64_t* __restrict__ out_a, int64_t* __restrict__ out_b, float* __restrict__ out_u2, float* __restrict__ out_v2,
                         int64_t* __restrict__ out_count) {
+  pdl_prologue();
   const int L = total[0];
   if (blockIdx.x == 0 && threadIdx.x == 0) out_count[0] = L;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L; i += gridDim.x * blockDim.x) {

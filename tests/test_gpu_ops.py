@@ -64,6 +64,8 @@ TC_CASES = [c for c in CONV_CASES if c[6] == 1] + [
     (2, 30, 40, 64, 128, 3, 2, 1, 1),      # layer2.0.conv1: stride 2 through TMA element strides; dgrad by zero insertion
     (1, 30, 40, 64, 128, 1, 2, 0, 1),      # layer2.0.downsample: 1x1 stride 2
     (1, 120, 160, 64, 128, 3, 2, 1, 1),    # the real layer2.0.conv1 size
+    (2, 24, 32, 64, 64, 3, 1, 1, 1),       # 64 -> 64 on a map of whole 8x16 tiles: the halo-tile kernel (resident weights), 2 images
+    (1, 120, 160, 64, 64, 3, 1, 1, 1),     # the real layer1 size through the halo-tile kernel: 150 tiles
 ]
 
 
