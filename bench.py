@@ -441,23 +441,25 @@ def run_ours(args, cfg):
         n0 = N.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        t_host = time.perf_counter()
         e0.record()
         for _ in range(args.steps):
             out = step(resident)
         e1.record()
+        host_ms = (time.perf_counter() - t_host) * 1e3        # time the host needed to ENQUEUE the steps (the GPU runs behind it)
         barrier()
         N.lib.ddn_profile_enable(0)
-        return max_over_ranks(e0.elapsed_time(e1)), N.launch_count() - n0, out
+        return max_over_ranks(e0.elapsed_time(e1)), N.launch_count() - n0, out, host_ms
 
     with ClockSampler(local_rank) as clk:
-        ms_total, launches, loss = timed_steps(False)
+        ms_total, launches, loss, host_ms = timed_steps(False)
     # ---- timed region 1b: the same K steps again with a CUDA-event pair around every convolution / loss kernel on the launching
     # stream (ddn_profile_*): the per-class kernel durations the roofline block is computed from
     if args.profile_run:      # under ncu: warm-up + the timed steps only, so the launch list is exactly `steps` steps
         if rank == 0:
             emit({"profile_run": True, "ms_per_step_under_profiler": ms_total / args.steps})
         return
-    ms_instrumented, _, _ = timed_steps(True)
+    ms_instrumented, _, _, _ = timed_steps(True)
     prof = N.profile_read()
 
     # ---- timed region 2: end to end from pinned host memory, loss read back every step.  Every step's inputs are copied
@@ -583,6 +585,7 @@ def run_ours(args, cfg):
                 "ms_per_step": ms_e2e / args.steps, "last_loss": last_loss},
         "gpu_launches": launches,
         "launches_per_step": launches / float(args.steps),
+        "host_enqueue_ms_per_step": host_ms / args.steps,
         "roofline": roof,
         "train_step_with_adam": {"value": pairs / (ms_adam / 1e3), "unit": "pairs/s", "ms_per_step": ms_adam / args.steps,
                                  "includes": "FusedAdam.step() over the flat arrays + the device-side fingerprint and re-pack of all bf16 weight "

@@ -664,6 +664,7 @@ struct TcHaloParams {
   int tiles_h, tiles_w, n_tiles;
   int imgs_per_group;
   BnFwdFinal fin;
+  TcBwdStats bst;
 };
 constexpr int HALO_TH = 8, HALO_TW = 16;
 constexpr int HALO_BH = HALO_TH + 2, HALO_BW = HALO_TW + 2;
@@ -828,6 +829,8 @@ conv64_halo_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     const int e = threadIdx.x - 64;
     const int ga = lane >> 3, gb = lane & 7;           // after the transpose: lane 8a+b holds rows 32q + 8a + i, channel quad b
     const bool stats = p.fin.a.acc != nullptr;
+    const bool bstats = p.bst.fin.a.acc != nullptr;     // data gradient: column sums of the BatchNorm backward that consumes `out`
+    double* const sum_acc = bstats ? p.bst.fin.a.acc : p.fin.a.acc;
     int k_it = 0;
     for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++k_it) {
       const int buf = k_it & 1;
@@ -846,18 +849,61 @@ conv64_halo_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           adv[i] = ad ? __ldg(reinterpret_cast<const float4*>(ad + i * row_stride + c * 32)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 rw[8];
+        uint2 yh[8];
+        if (bstats) {
+          const size_t boff = pix0 * 64 + gb * 4 + c * 32;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            rw[i] = __ldg(reinterpret_cast<const float4*>(p.bst.raw + boff + i * row_stride));
+            if (p.bst.y_hi) yh[i] = __ldg(reinterpret_cast<const uint2*>(p.bst.y_hi + boff + i * row_stride));
+          }
+        }
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 64 + c * 32), v);
         transpose_8x8_quads(v, lane);
         float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+        if (bstats) {      // same arithmetic as the epilogue of conv_tc_kernel / bn_colsum_kernel<1>
+          const int grp = n / p.imgs_per_group;
+          const float4 mu = __ldg(reinterpret_cast<const float4*>(p.bst.mean + (size_t)grp * 64 + c * 32 + gb * 4));
+          const float4 is = __ldg(reinterpret_cast<const float4*>(p.bst.invstd + (size_t)grp * 64 + c * 32 + gb * 4));
+          float4 scl = make_float4(0.f, 0.f, 0.f, 0.f), be = scl;
+          if (!p.bst.y_hi && p.bst.relu) {
+            const float4 gm = __ldg(reinterpret_cast<const float4*>(p.bst.gamma + c * 32 + gb * 4));
+            be = __ldg(reinterpret_cast<const float4*>(p.bst.beta + c * 32 + gb * 4));
+            scl = make_float4(gm.x * is.x, gm.y * is.y, gm.z * is.z, gm.w * is.w);
+          }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 raw = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
-          *reinterpret_cast<float4*>(o + i * row_stride + c * 32) = make_float4(raw.x + adv[i].x, raw.y + adv[i].y, raw.z + adv[i].z, raw.w + adv[i].w);
-          s1.x += raw.x; s1.y += raw.y; s1.z += raw.z; s1.w += raw.w;
-          s2.x = fmaf(raw.x, raw.x, s2.x); s2.y = fmaf(raw.y, raw.y, s2.y); s2.z = fmaf(raw.z, raw.z, s2.z); s2.w = fmaf(raw.w, raw.w, s2.w);
+          for (int i = 0; i < 8; ++i) {
+            float4 g = make_float4(__uint_as_float(v[4 * i]) + adv[i].x, __uint_as_float(v[4 * i + 1]) + adv[i].y,
+                                   __uint_as_float(v[4 * i + 2]) + adv[i].z, __uint_as_float(v[4 * i + 3]) + adv[i].w);
+            *reinterpret_cast<float4*>(o + i * row_stride + c * 32) = g;
+            if (p.bst.y_hi) {
+              const uint2 hh = yh[i];
+              if ((hh.x & 0x8000u) || !(hh.x & 0x7fffu)) g.x = 0.f;
+              if ((hh.x & 0x80000000u) || !(hh.x & 0x7fff0000u)) g.y = 0.f;
+              if ((hh.y & 0x8000u) || !(hh.y & 0x7fffu)) g.z = 0.f;
+              if ((hh.y & 0x80000000u) || !(hh.y & 0x7fff0000u)) g.w = 0.f;
+            } else if (p.bst.relu) {
+              if (!(fmaf(rw[i].x - mu.x, scl.x, be.x) > 0.f)) g.x = 0.f;
+              if (!(fmaf(rw[i].y - mu.y, scl.y, be.y) > 0.f)) g.y = 0.f;
+              if (!(fmaf(rw[i].z - mu.z, scl.z, be.z) > 0.f)) g.z = 0.f;
+              if (!(fmaf(rw[i].w - mu.w, scl.w, be.w) > 0.f)) g.w = 0.f;
+            }
+            s1.x += g.x; s1.y += g.y; s1.z += g.z; s1.w += g.w;
+            s2.x = fmaf(g.x, (rw[i].x - mu.x) * is.x, s2.x); s2.y = fmaf(g.y, (rw[i].y - mu.y) * is.y, s2.y);
+            s2.z = fmaf(g.z, (rw[i].z - mu.z) * is.z, s2.z); s2.w = fmaf(g.w, (rw[i].w - mu.w) * is.w, s2.w);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 raw = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+            *reinterpret_cast<float4*>(o + i * row_stride + c * 32) = make_float4(raw.x + adv[i].x, raw.y + adv[i].y, raw.z + adv[i].z, raw.w + adv[i].w);
+            s1.x += raw.x; s1.y += raw.y; s1.z += raw.z; s1.w += raw.w;
+            s2.x = fmaf(raw.x, raw.x, s2.x); s2.y = fmaf(raw.y, raw.y, s2.y); s2.z = fmaf(raw.z, raw.z, s2.z); s2.w = fmaf(raw.w, raw.w, s2.w);
+          }
         }
-        if (stats) {      // 8 rows summed locally; the other 24 rows of this warp sit in lanes b + 8, b + 16, b + 24
+        if (stats || bstats) {      // 8 rows summed locally; the other 24 rows of this warp sit in lanes b + 8, b + 16, b + 24
 #pragma unroll
           for (int off = 8; off < 32; off <<= 1) {
             s1.x += __shfl_xor_sync(0xffffffffu, s1.x, off); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, off);
@@ -874,15 +920,19 @@ conv64_halo_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
-      if (stats) {
+      if (stats || bstats) {
         asm volatile("bar.sync 1, 128;" ::: "memory");
         const int grp = n / p.imgs_per_group;          // a tile lies inside one image
         const int col = e & 63, k = e >> 6;            // 128 threads = 64 columns x {sum, sum of squares}
         const float s4 = s_part[buf][k][0][col] + s_part[buf][k][1][col] + s_part[buf][k][2][col] + s_part[buf][k][3][col];
-        red_add_f64(p.fin.a.acc + (size_t)(grp * 2 + k) * 64 + col, (double)s4);
+        red_add_f64(sum_acc + (size_t)(grp * 2 + k) * 64 + col, (double)s4);
       }
     }
-    if (stats) {
+    if (bstats) {
+      const bool last = bn_last_cta(p.bst.fin.a.ticket, gridDim.x, e == 0, &s_last, [] { asm volatile("bar.sync 1, 128;" ::: "memory"); });
+      if (last)
+        for (int c = e; c < 64; c += 128) bn_bwd_finalize_channel(p.bst.fin, c);
+    } else if (stats) {
       const bool last = bn_last_cta(p.fin.a.ticket, gridDim.x, e == 0, &s_last, [] { asm volatile("bar.sync 1, 128;" ::: "memory"); });
       if (last)
         for (int c = e; c < 64; c += 128) bn_fwd_finalize_channel(p.fin, c);
@@ -1839,7 +1889,7 @@ int tc_conv_planes(TcPlanes in, const float* w_oihw, const TcPlanes* wpk, float*
     DDN_LAUNCH(pack_weights_tc_kernel, wblocks, 256, 0, st, w_oihw, ph, pl, Cout, Cin, k, dgrad, want_lo);
     b_hi = ph; b_lo = pl;
   }
-  if (tc_halo_enabled() && k == 3 && gin == 64 && gout == 64 && stride == 1 && dil == 1 && !ep && !bst && Ho % HALO_TH == 0 && Wo % HALO_TW == 0) {
+  if (tc_halo_enabled() && k == 3 && gin == 64 && gout == 64 && stride == 1 && dil == 1 && !ep && Ho % HALO_TH == 0 && Wo % HALO_TW == 0) {
     // 64 -> 64 channels (layer1): resident weights + one halo tile per 8x16 output pixels (conv64_halo_kernel)
     TcHaloParams hp;
     memset(&hp, 0, sizeof(hp));
@@ -1851,6 +1901,13 @@ int tc_conv_planes(TcPlanes in, const float* w_oihw, const TcPlanes* wpk, float*
       DDN_CHECK_ARG(!dgrad && stats->G >= 1 && stats->G <= BN_MAX_GROUPS && N % stats->G == 0 && stats->C == 64, "bad BatchNorm statistics request");
       hp.fin = *stats;
       hp.imgs_per_group = N / stats->G;
+    }
+    if (bst) {
+      DDN_CHECK_ARG(dgrad && !stats && bst->raw && bst->mean && bst->invstd && bst->fin.a.acc && bst->fin.G >= 1 && bst->fin.G <= BN_MAX_GROUPS &&
+                    N % bst->fin.G == 0 && bst->fin.C == 64 && (bst->y_hi || !bst->relu || (bst->gamma && bst->beta)),
+                    "bad BatchNorm backward-statistics request");
+      hp.bst = *bst;
+      hp.imgs_per_group = N / bst->fin.G;
     }
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     DDN_TRY(make_act_map_halo(&ma_hi, in.hi, N, H, W, 64));

@@ -549,11 +549,11 @@ static int bn_backward_for(const Ctx& c, const BnSpec& bs, const ConvBufs& cb, c
 }
 
 // Column sums of BatchNorm `bs` (y = relu(bn(raw) [+ residual])) computed by the epilogue of the tensor-core data gradient that
-// produces its dY (conv_tc.cuh TcBwdStats) instead of a separate pass over dY and raw.  Layers narrower than
-// DDN_FUSE_BWD_STATS_MINC channels keep the separate pass: their data gradients are epilogue-bound already.
+// produces its dY (conv_tc.cuh TcBwdStats) instead of a separate pass over dY and raw.  DDN_FUSE_BWD_STATS_MINC (default 64 = every
+// layer) keeps the separate pass for layers narrower than that many channels (A/B switch).
 static int fuse_bwd_stats_min_c() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("DDN_FUSE_BWD_STATS_MINC"); v = e ? atoi(e) : 128; if (v < 0) v = 0; }
+  if (v < 0) { const char* e = getenv("DDN_FUSE_BWD_STATS_MINC"); v = e ? atoi(e) : 64; if (v < 0) v = 0; }
   return v;
 }
 static bool bwd_stats_for(const Ctx& c, const BnSpec& bs, const ConvBufs& cb, const __nv_bfloat16* y_hi, int slot, TcBwdStats* out) {

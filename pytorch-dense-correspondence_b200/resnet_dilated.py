@@ -141,7 +141,7 @@ class _Backbone(torch.autograd.Function):
         cb = N.NO_BUCKET_CALLBACK
         if hook is not None:
             if owner._pad_index is not None:     # the padding words travel through the all-reduce: define them
-                grads.index_fill_(0, owner._pad_index.to(grads.device), 0.0)
+                grads.index_fill_(0, owner._pad_index_on(grads.device), 0.0)
             sc = hook.cotangent_scale()          # the mean over ranks, folded into the (linear) backward
             dy = dy * sc if dy is not None else None
             dlow = dlow * sc if dlow is not None else None
@@ -156,7 +156,7 @@ class _Backbone(torch.autograd.Function):
             hook.finish(grads)
         ps = owner._params
         if hook is None and owner._pad_index is not None:   # alignment padding between tensors: keep it zero (it is all-reduced / stepped too)
-            grads.index_fill_(0, owner._pad_index.to(grads.device), 0.0)
+            grads.index_fill_(0, owner._pad_index_on(grads.device), 0.0)
         wants = ctx.needs_input_grad[3:]
         for p, want, (_, _, o, n) in zip(ps, wants, owner._ptab):
             if not want:
@@ -184,6 +184,12 @@ class _Backbone(torch.autograd.Function):
 
 
 class Resnet34_8s(nn.Module):
+    def _pad_index_on(self, device):
+        t = self._pad_index_dev.get(device)
+        if t is None:
+            t = self._pad_index_dev[device] = self._pad_index.to(device)
+        return t
+
     def __init__(self, num_classes=1000, precision=None):
         super().__init__()
         if not (1 <= num_classes <= 32):
@@ -202,6 +208,7 @@ class Resnet34_8s(nn.Module):
         for (_, _, off, n) in self._ptab:
             pads += list(range(off + n, (off + n + 3) // 4 * 4))
         self._pad_index = torch.tensor(pads, dtype=torch.long) if pads else None
+        self._pad_index_dev = {}      # device -> resident copy (a pageable .to(device) inside backward would stall the host on the stream)
         self._wcache = None
         self._wcache_nonce = 0
         self._bucket_hook = None      # data_parallel.GradientAllReducer: called per finished gradient bucket during backward
