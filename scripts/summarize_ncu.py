@@ -46,6 +46,8 @@ def launches(tag, path):
 
 def report(tag, path):
     base = os.path.splitext(os.path.basename(path))[0]
+    if base.startswith(tag + "_"):
+        base = base[len(tag) + 1:]
     raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]

@@ -461,7 +461,8 @@ def test_triplet_loss_matches_the_oracle():
 
 
 @pytest.mark.parametrize("D,over", [(3, {}), (16, {}), (8, {"use_l2_pixel_loss_on_masked_non_matches": True, "M_pixel": 9,
-                                                        "scale_by_hard_negatives": False})])
+                                                        "scale_by_hard_negatives": False}),
+                                    (32, {}), (5, {}), (16, {"use_l2_pixel_loss_on_masked_non_matches": True, "M_pixel": 25})])
 def test_loss_fused_with_the_upsample_equals_the_generic_loss(D, over):
     """csrc/loss_lowres.cu: the loss evaluated through the bilinear upsample (4 low-resolution cells per sampled pixel) must equal
     the loss gathered from the upsampled image -- all five outputs, hard-negative counts -- and its gradient w.r.t. the
