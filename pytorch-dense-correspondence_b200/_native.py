@@ -45,6 +45,7 @@ class WithinSceneCfg(ctypes.Structure):
 
 _SIGNATURES = {
     "ddn_abi_version": (i32, []),
+    "ddn_set_reserved_sms": (i32, [i32]),
     "ddn_last_error": (ctypes.c_char_p, []),
     "ddn_kernel_launch_count": (i64, []),
     "ddn_resnet34_8s_param_table": (i32, [i32, ctypes.POINTER(TensorEntry), i32]),

@@ -80,6 +80,7 @@ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 
 int num_sms();
+int tc_worker_sms();      // num_sms() minus the SMs reserved for a concurrent collective (ddn_set_reserved_sms)
 
 // Optional per-kernel-class timing with CUDA events on the launching stream (off by default; bench.py turns it on).
 enum ProfClass { PROF_CONV_FWD_SIMT = 0, PROF_CONV_DGRAD_SIMT, PROF_CONV_WGRAD_SIMT, PROF_CONV_FWD_TC, PROF_CONV_DGRAD_TC,

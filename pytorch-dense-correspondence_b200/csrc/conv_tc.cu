@@ -665,6 +665,8 @@ struct TcHaloParams {
   int imgs_per_group;
   BnFwdFinal fin;
   TcBwdStats bst;
+  const float* ep_scale; const float* ep_shift; int ep_relu;      // folded inference epilogue (see TcConvParams)
+  __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
 };
 constexpr int HALO_TH = 8, HALO_TW = 16;
 constexpr int HALO_BH = HALO_TH + 2, HALO_BW = HALO_TW + 2;
@@ -863,7 +865,26 @@ conv64_halo_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 64 + c * 32), v);
         transpose_8x8_quads(v, lane);
         float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
-        if (bstats) {      // same arithmetic as the epilogue of conv_tc_kernel / bn_colsum_kernel<1>
+        if (p.ep_scale) {        // inference: eval-mode BatchNorm folded in, + residual, ReLU; fp32 and / or the next conv's planes
+          const float4 sc = __ldg(reinterpret_cast<const float4*>(p.ep_scale + c * 32 + gb * 4));
+          const float4 sf = __ldg(reinterpret_cast<const float4*>(p.ep_shift + c * 32 + gb * 4));
+          const size_t eoff = pix0 * 64 + gb * 4 + c * 32;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 f = make_float4(fmaf(__uint_as_float(v[4 * i]), sc.x, sf.x) + adv[i].x, fmaf(__uint_as_float(v[4 * i + 1]), sc.y, sf.y) + adv[i].y,
+                                   fmaf(__uint_as_float(v[4 * i + 2]), sc.z, sf.z) + adv[i].z, fmaf(__uint_as_float(v[4 * i + 3]), sc.w, sf.w) + adv[i].w);
+            if (p.ep_relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f); }
+            if (p.out) *reinterpret_cast<float4*>(p.out + eoff + i * row_stride) = f;
+            if (p.out_hi) {
+              const __nv_bfloat16 h0 = __float2bfloat16_rn(f.x), h1 = __float2bfloat16_rn(f.y), h2 = __float2bfloat16_rn(f.z), h3 = __float2bfloat16_rn(f.w);
+              *reinterpret_cast<uint2*>(p.out_hi + eoff + i * row_stride) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+              if (p.out_lo)
+                *reinterpret_cast<uint2*>(p.out_lo + eoff + i * row_stride) =
+                    make_uint2(pack_bf16x2(__float2bfloat16_rn(f.x - __bfloat162float(h0)), __float2bfloat16_rn(f.y - __bfloat162float(h1))),
+                               pack_bf16x2(__float2bfloat16_rn(f.z - __bfloat162float(h2)), __float2bfloat16_rn(f.w - __bfloat162float(h3))));
+            }
+          }
+        } else if (bstats) {      // same arithmetic as the epilogue of conv_tc_kernel / bn_colsum_kernel<1>
           const int grp = n / p.imgs_per_group;
           const float4 mu = __ldg(reinterpret_cast<const float4*>(p.bst.mean + (size_t)grp * 64 + c * 32 + gb * 4));
           const float4 is = __ldg(reinterpret_cast<const float4*>(p.bst.invstd + (size_t)grp * 64 + c * 32 + gb * 4));
@@ -1677,7 +1698,7 @@ int tc_wgrad_planes(TcPlanes x, TcPlanes dy, float* dw, int N, int H, int W, int
     DDN_TRY(make_act_map_hw(&md_lo, want_lo ? dy.lo : dy.hi, N, H, W, 64, HALO_TH, HALO_TW));
     const int nsplit = want_lo ? 2 : 1;
     const size_t smem = (size_t)2 * nsplit * (WGH_X_SLOT + WGH_DY_BYTES) + 1024;
-    const int grid = std::min(hp.n_tiles, num_sms());
+    const int grid = std::min(hp.n_tiles, tc_worker_sms());
     {
       ProfScope ps(PROF_CONV_WGRAD_TC, 2.0 * N * H * W * 64.0 * 9 * 64, st);
       if (want_lo) {
@@ -1708,7 +1729,7 @@ int tc_wgrad_planes(TcPlanes x, TcPlanes dy, float* dw, int N, int H, int W, int
   const int total_kb = N * p.tiles_h * p.tiles_w;
   const int ctas_xy = (Cin / bn) * (k == 3 ? 3 : 1) * (int)ceil_div(Cout, 128);
   // split-K so that the grid is (just under) a whole number of waves: 1 CTA per SM resident, no ragged tail wave
-  const int sms = num_sms();
+  const int sms = tc_worker_sms();
   int waves = ctas_xy > sms ? 1 : (total_kb >= 64 * (sms / ctas_xy) ? 2 : 1);
   int splits = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)waves * sms / ctas_xy, ceil_div(total_kb, 4)));
   p.kb_per_split = (int)ceil_div(total_kb, splits);
@@ -1853,7 +1874,7 @@ static int launch_conv64_halo(const CUtensorMap& a_hi, const CUtensorMap& a_lo, 
     DDN_CUDA(cudaFuncSetAttribute(conv64_halo_kernel<NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  const int grid = std::min(p.n_tiles, num_sms());
+  const int grid = std::min(p.n_tiles, tc_worker_sms());
   DDN_LAUNCH((conv64_halo_kernel<NPROD>), grid, TC_THREADS, smem, st, a_hi, a_lo, b_hi, b_lo, p);
   return 0;
 }
@@ -1889,11 +1910,16 @@ int tc_conv_planes(TcPlanes in, const float* w_oihw, const TcPlanes* wpk, float*
     DDN_LAUNCH(pack_weights_tc_kernel, wblocks, 256, 0, st, w_oihw, ph, pl, Cout, Cin, k, dgrad, want_lo);
     b_hi = ph; b_lo = pl;
   }
-  if (tc_halo_enabled() && k == 3 && gin == 64 && gout == 64 && stride == 1 && dil == 1 && !ep && Ho % HALO_TH == 0 && Wo % HALO_TW == 0) {
+  if (tc_halo_enabled() && k == 3 && gin == 64 && gout == 64 && stride == 1 && dil == 1 && Ho % HALO_TH == 0 && Wo % HALO_TW == 0) {
     // 64 -> 64 channels (layer1): resident weights + one halo tile per 8x16 output pixels (conv64_halo_kernel)
     TcHaloParams hp;
     memset(&hp, 0, sizeof(hp));
-    DDN_CHECK_ARG(out != nullptr, "conv output pointer is null");
+    if (ep) {
+      DDN_CHECK_ARG(!dgrad && !stats && !bst && ep->scale && ep->shift && (out || ep->out_hi), "folded epilogue: forward only, needs scale/shift and an output");
+      hp.ep_scale = ep->scale; hp.ep_shift = ep->shift; hp.ep_relu = ep->relu; hp.out_hi = ep->out_hi; hp.out_lo = want_lo ? ep->out_lo : nullptr;
+    } else {
+      DDN_CHECK_ARG(out != nullptr, "conv output pointer is null");
+    }
     hp.out = out; hp.addend = addend; hp.N = N; hp.H = Ho; hp.W = Wo;
     hp.tiles_h = Ho / HALO_TH; hp.tiles_w = Wo / HALO_TW; hp.n_tiles = N * hp.tiles_h * hp.tiles_w;
     hp.imgs_per_group = N;
@@ -1928,7 +1954,7 @@ int tc_conv_planes(TcPlanes in, const float* w_oihw, const TcPlanes* wpk, float*
   p.n_co = gout / block_n;
   const int subs_per_tile = pair ? 4 : 2;
   const int tiles = (int)ceil_div(p.n_sub, subs_per_tile) * p.n_co;
-  const int workers_max = pair ? num_sms() / 2 : num_sms();
+  const int workers_max = pair ? tc_worker_sms() / 2 : tc_worker_sms();
   // the tiles of the last, partial wave are cut along N so that the tail costs a fraction of a tile time
   const int rem = tiles % workers_max;
   const int min_width = pair ? 64 : 32;

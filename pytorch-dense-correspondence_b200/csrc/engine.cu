@@ -30,6 +30,17 @@ bool pdl_enabled() {
   return v != 0;
 }
 
+// SMs left free by the persistent tcgen05 kernels (one CTA per SM, no room for a second): while a data-parallel host has a gradient
+// all-reduce in flight, NCCL's CTAs need somewhere to run -- without the reservation they take SMs between two of our launches and
+// the next persistent kernel runs a whole extra wave for the CTAs that found no SM.  Set by ddn_set_reserved_sms (DDN_RESERVED_SMS).
+static std::atomic<int> g_reserved_sms{-1};
+int tc_worker_sms() {
+  int r = g_reserved_sms.load(std::memory_order_relaxed);
+  if (r < 0) { const char* e = getenv("DDN_RESERVED_SMS"); r = e ? atoi(e) : 0; if (r < 0) r = 0; g_reserved_sms.store(r); }
+  const int n = num_sms();
+  return r >= n - 8 ? 8 : n - r;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -675,6 +686,11 @@ static int net_backward(const Ctx& c, const float* dy, const float* dlow_nhwc, d
 using namespace ddn;
 
 extern "C" int ddn_abi_version(void) { return DDN_ABI_VERSION; }
+extern "C" int ddn_set_reserved_sms(int n) {
+  DDN_CHECK_ARG(n >= 0 && n <= 64, "reserved SM count must be in [0, 64]");
+  g_reserved_sms.store(n);
+  return 0;
+}
 extern "C" const char* ddn_last_error(void) { return g_err; }
 extern "C" int64_t ddn_kernel_launch_count(void) { return g_launches.load(); }
 

@@ -24,6 +24,11 @@ def init_from_env(backend=None):
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local_rank)
+            # opt-in experiment (DDN_RESERVED_SMS=n): cap NCCL at n CTAs and keep n SMs free of the persistent kernels for them.
+            # Measured on 2 x B200 (profiles/r2_reserved_sms_ab.md): 0 -> 549.5, 4 -> 543.6, 8 -> 534.7, 16 -> 520.8 pairs/s; the
+            # reservation costs every kernel of the step, the all-reduce only overlaps a few of them.  Default 0.
+            if int(os.environ.get("DDN_RESERVED_SMS", "0")) > 0:
+                os.environ.setdefault("NCCL_MAX_CTAS", os.environ["DDN_RESERVED_SMS"])
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
         dist.init_process_group(backend=backend, rank=rank, world_size=world)
@@ -102,8 +107,16 @@ class GradientAllReducer(object):
         self.module = module
         if module is not None and overlap and dist.is_initialized() and dist.get_world_size(group) > 1:
             module._bucket_hook = self
+            self._reserve_sms(int(os.environ.get("DDN_RESERVED_SMS", "0")))
         elif module is not None:
             module._bucket_hook = None
+
+    @staticmethod
+    def _reserve_sms(n):
+        """SMs the persistent tensor-core kernels leave free for NCCL while an all-reduce overlaps the backward."""
+        if torch.cuda.is_available():
+            from . import _native as N
+            N.check(N.lib.ddn_set_reserved_sms(int(n)))
 
     # ---- overlapped path: called by resnet_dilated._Backbone.backward
     def cotangent_scale(self):
@@ -129,6 +142,7 @@ class GradientAllReducer(object):
     def detach(self):
         if self.module is not None and getattr(self.module, "_bucket_hook", None) is self:
             self.module._bucket_hook = None
+            self._reserve_sms(0)
 
     # ---- explicit path
     def __call__(self):
