@@ -34,9 +34,20 @@ bool pdl_enabled() {
 // all-reduce in flight, NCCL's CTAs need somewhere to run -- without the reservation they take SMs between two of our launches and
 // the next persistent kernel runs a whole extra wave for the CTAs that found no SM.  Set by ddn_set_reserved_sms (DDN_RESERVED_SMS).
 static std::atomic<int> g_reserved_sms{-1};
+// ... and the same for a WINDOW only: from the first gradient bucket a backward hands to its host (whose all-reduce then runs
+// concurrently) to the end of that backward (DDN_OVERLAP_RESERVED_SMS = n; the host then caps NCCL at n CTAs).  Measured on
+// 2 x B200 in one call (profiles/r2_reserved_sms_ab.md): n = 0 538, n = 4 545, n = 8 537, n = 16 528 pairs/s -- inside the +-1 %
+// run-to-run noise, so the default is 0 (no reservation, NCCL's own CTA count).
+static std::atomic<int> g_window_reserved{0};
+static int overlap_window_sms() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DDN_OVERLAP_RESERVED_SMS"); v = e ? atoi(e) : 0; if (v < 0 || v > 64) v = 0; }
+  return v;
+}
 int tc_worker_sms() {
   int r = g_reserved_sms.load(std::memory_order_relaxed);
   if (r < 0) { const char* e = getenv("DDN_RESERVED_SMS"); r = e ? atoi(e) : 0; if (r < 0) r = 0; g_reserved_sms.store(r); }
+  r = std::max(r, g_window_reserved.load(std::memory_order_relaxed));
   const int n = num_sms();
   return r >= n - 8 ? 8 : n - r;
 }
@@ -603,10 +614,14 @@ static int net_backward(const Ctx& c, const float* dy, const float* dlow_nhwc, d
   };
   int64_t bucket_end = s.n_params;
   int bucket_id = 0;
+  struct WindowGuard { ~WindowGuard() { g_window_reserved.store(0, std::memory_order_relaxed); } } window_guard;
   auto close_bucket = [&](int64_t begin) -> int {
     if (!pending.empty()) DDN_TRY(tc_unpack_wgrads(pending.data(), (int)pending.size(), c.f(p.dwp_all), c.grads, c.st));
     pending.clear();
-    if (on_bucket) on_bucket(user, bucket_id, begin, bucket_end - begin);
+    if (on_bucket) {
+      on_bucket(user, bucket_id, begin, bucket_end - begin);
+      g_window_reserved.store(overlap_window_sms(), std::memory_order_relaxed);     // a collective is in flight from here on
+    }
     ++bucket_id; bucket_end = begin;
     return 0;
   };

@@ -24,11 +24,12 @@ def init_from_env(backend=None):
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local_rank)
-            # opt-in experiment (DDN_RESERVED_SMS=n): cap NCCL at n CTAs and keep n SMs free of the persistent kernels for them.
-            # Measured on 2 x B200 (profiles/r2_reserved_sms_ab.md): 0 -> 549.5, 4 -> 543.6, 8 -> 534.7, 16 -> 520.8 pairs/s; the
-            # reservation costs every kernel of the step, the all-reduce only overlaps a few of them.  Default 0.
-            if int(os.environ.get("DDN_RESERVED_SMS", "0")) > 0:
-                os.environ.setdefault("NCCL_MAX_CTAS", os.environ["DDN_RESERVED_SMS"])
+            # Experiments, both off by default (profiles/r2_reserved_sms_ab.md): DDN_OVERLAP_RESERVED_SMS=n keeps n SMs free of the
+            # persistent kernels from the first gradient bucket to the end of the backward, DDN_RESERVED_SMS=n for the whole step;
+            # NCCL is then capped at n CTAs so that it fits there.
+            cap = max(int(os.environ.get("DDN_OVERLAP_RESERVED_SMS", "0")), int(os.environ.get("DDN_RESERVED_SMS", "0")))
+            if cap > 0:
+                os.environ.setdefault("NCCL_MAX_CTAS", str(cap))
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
         dist.init_process_group(backend=backend, rank=rank, world_size=world)
