@@ -245,6 +245,97 @@ int launch_nchw_to_nhwc4(const float* x, float* y, int N, int H, int W, cudaStre
     else { CALL(32); }                    \
   } while (0)
 
+// Plane variant of fc_wgrad_kernel for C = 512 and D <= 8: 64 threads x 8 channels (one 16-byte load per plane and pixel) cover a
+// pixel, the 4 thread groups of a block walk 4 pixels at a time and two are in flight per thread -- the scalar version above moves
+// 2 bytes per load and runs at 1/7 of the HBM rate on the 157 MB feature map.
+template <int DM>
+__global__ void __launch_bounds__(256)
+fc_wgrad_planes_kernel(const float* __restrict__ dlow, const __nv_bfloat16* __restrict__ feat_hi, const __nv_bfloat16* __restrict__ feat_lo,
+                       float* __restrict__ dw, float* __restrict__ dbias, int64_t Mimg, int N, int D, int pix_per_block) {
+  pdl_prologue();
+  constexpr int C = 512;
+  const int64_t total = (int64_t)N * Mimg;
+  const int64_t p0 = (int64_t)blockIdx.x * pix_per_block;
+  const int64_t p1 = min(total, p0 + pix_per_block);
+  const int cq = threadIdx.x & 63, rr = threadIdx.x >> 6;
+  float acc[8][DM];
+  float bsum[DM];
+#pragma unroll
+  for (int d = 0; d < DM; ++d) {
+    bsum[d] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j][d] = 0.f;
+  }
+  auto fma_pixel = [&](const uint4 h, const uint4 l, const float (&g)[DM]) {
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      // bf16 -> fp32 is a 16-bit shift; feature = hi + lo
+      const float f0 = __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
+      const float f1 = __uint_as_float(hw[j] & 0xffff0000u) + __uint_as_float(lw[j] & 0xffff0000u);
+#pragma unroll
+      for (int d = 0; d < DM; ++d) { acc[2 * j][d] = fmaf(g[d], f0, acc[2 * j][d]); acc[2 * j + 1][d] = fmaf(g[d], f1, acc[2 * j + 1][d]); }
+    }
+  };
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (int64_t pix = p0 + rr; pix < p1; pix += 8) {
+    const int64_t pa = pix, pb = pix + 4;
+    const bool hb = pb < p1;
+    const uint4 ha = __ldg(reinterpret_cast<const uint4*>(feat_hi + pa * C) + cq);
+    const uint4 la = feat_lo ? __ldg(reinterpret_cast<const uint4*>(feat_lo + pa * C) + cq) : z;
+    const uint4 hbv = hb ? __ldg(reinterpret_cast<const uint4*>(feat_hi + pb * C) + cq) : z;
+    const uint4 lbv = (hb && feat_lo) ? __ldg(reinterpret_cast<const uint4*>(feat_lo + pb * C) + cq) : z;
+    float ga[DM], gb[DM];
+    const int64_t na = pa / Mimg, qa = pa - na * Mimg, nb = hb ? pb / Mimg : 0, qb = hb ? pb - nb * Mimg : 0;
+#pragma unroll
+    for (int d = 0; d < DM; ++d) {
+      ga[d] = d < D ? __ldg(dlow + (na * D + d) * Mimg + qa) : 0.f;
+      gb[d] = (hb && d < D) ? __ldg(dlow + (nb * D + d) * Mimg + qb) : 0.f;
+    }
+    fma_pixel(ha, la, ga);
+    fma_pixel(hbv, lbv, gb);
+    if (cq == 0) {
+#pragma unroll
+      for (int d = 0; d < DM; ++d) bsum[d] += ga[d] + gb[d];
+    }
+  }
+  // the 4 pixel groups of the block are folded through shared memory one after the other, then one atomic per (d, c)
+  __shared__ float s_acc[DM][C];
+  __shared__ float s_b[4][DM];
+  if (cq == 0) {
+#pragma unroll
+    for (int d = 0; d < DM; ++d) s_b[rr][d] = bsum[d];
+  }
+  for (int r = 1; r < 4; ++r) {
+    if (rr == r) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int d = 0; d < DM; ++d) s_acc[d][cq * 8 + j] = acc[j][d];
+    }
+    __syncthreads();
+    if (rr == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int d = 0; d < DM; ++d) acc[j][d] += s_acc[d][cq * 8 + j];
+    }
+    __syncthreads();
+  }
+  if (rr == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int d = 0; d < DM; ++d)
+        if (d < D) atomicAdd(dw + d * C + cq * 8 + j, acc[j][d]);
+    if (cq == 0) {
+#pragma unroll
+      for (int d = 0; d < DM; ++d)
+        if (d < D) atomicAdd(dbias + d, s_b[0][d] + s_b[1][d] + s_b[2][d] + s_b[3][d]);
+    }
+  }
+}
+
 int launch_fc_forward(const float* feat, const __nv_bfloat16* feat_hi, const __nv_bfloat16* feat_lo, const float* w, const float* bias,
                       float* low, float* low_nhwc, int64_t Mimg, int N, int C, int D, cudaStream_t st) {
   DDN_CHECK_ARG(feat || feat_hi, "fc: no feature tensor");
@@ -274,6 +365,11 @@ int launch_fc_backward(const float* dlow, const float* feat, const __nv_bfloat16
   DDN_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * D, st));
   int ppb = (int)std::max<int64_t>(16, ceil_div(total, (int64_t)num_sms() * 4));
   int blocks = (int)ceil_div(total, ppb);
+  if (!feat && C == 512 && D <= 8) {
+    if (D <= 4) DDN_LAUNCH(fc_wgrad_planes_kernel<4>, blocks, 256, 0, st, dlow, feat_hi, feat_lo, dw, dbias, Mimg, N, D, ppb);
+    else DDN_LAUNCH(fc_wgrad_planes_kernel<8>, blocks, 256, 0, st, dlow, feat_hi, feat_lo, dw, dbias, Mimg, N, D, ppb);
+    return 0;
+  }
 #define CALL(DM) DDN_LAUNCH(fc_wgrad_kernel<DM>, blocks, 256, 0, st, dlow, feat, feat_hi, feat_lo, dw, dbias, Mimg, N, C, D, ppb)
   FC_DISPATCH(D, CALL);
 #undef CALL
