@@ -1943,8 +1943,12 @@ int tc_conv_planes(TcPlanes in, const float* w_oihw, const TcPlanes* wpk, float*
     ProfScope ps(dgrad ? PROF_CONV_DGRAD_TC : PROF_CONV_FWD_TC, fl, st);
     return want_lo ? launch_conv64_halo<3>(ma_hi, ma_lo, mb_hi, mb_lo, hp, st) : launch_conv64_halo<1>(ma_hi, ma_lo, mb_hi, mb_lo, hp, st);
   }
-  const bool pair = tc_pair_enabled() && gout % 256 == 0;
-  const int block_n = pair ? 256 : gout % 128 == 0 ? 128 : 64;
+  // CTA pairs for Cout % 256 == 0 (256 x 256 tiles).  DDN_TC_PAIR128=1 also pairs Cout = 128 (layer2, 256 x 128 tiles: each CTA
+  // stages half of the weight rows, 25 % less L2 -> SM traffic per pixel on a layer that runs at that throughput cap): parity-green,
+  // but 279.7 vs 279.3 pairs/s in a 3 x 2 one-call A/B -- noise -- so the single-CTA 128 x 128 tiles stay the default.
+  static const bool pair128 = [] { const char* e = getenv("DDN_TC_PAIR128"); return e && e[0] == '1'; }();
+  const bool pair = tc_pair_enabled() && (gout % 256 == 0 || (pair128 && gout == 128));
+  const int block_n = pair ? (gout % 256 == 0 ? 256 : 128) : gout % 128 == 0 ? 128 : 64;
   TcConvParams p;
   memset(&p, 0, sizeof(p));
   p.out = out; p.addend = addend; p.N = N; p.H = Ho; p.W = Wo; p.Cin = gin; p.Cout = gout; p.taps_w = k; p.dil = dil;
@@ -1996,7 +2000,8 @@ int tc_conv_planes(TcPlanes in, const float* w_oihw, const TcPlanes* wpk, float*
 #define CONV_TC(BN, PR)                                                                                                       \
   (want_lo ? launch_conv_tc<BN, 3, PR>(ma_hi, ma_lo, mb_hi, mb_lo, mt_hi, mt_lo, p, workers, st)                               \
            : launch_conv_tc<BN, 1, PR>(ma_hi, ma_lo, mb_hi, mb_lo, mt_hi, mt_lo, p, workers, st))
-  if (pair) return CONV_TC(256, true);
+  if (pair && block_n == 256) return CONV_TC(256, true);
+  if (pair) return CONV_TC(128, true);
   if (block_n == 128) return CONV_TC(128, false);
   return CONV_TC(64, false);
 #undef CONV_TC
