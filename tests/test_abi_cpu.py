@@ -73,6 +73,9 @@ def test_workspace_and_argument_checks():
     assert N.lib.ddn_conv2d_workspace_bytes(1, 60, 80, 64, 64, 3, 1, 1, 1, 0) >= 3 * 9 * 64 * 64 * 4
     assert N.lib.ddn_batchnorm_workspace_bytes(4800, 6) == 0 and N.lib.ddn_batchnorm_workspace_bytes(4800, 512) > 0
     assert N.launch_count() == before
+    # SM reservation for a concurrent collective: a host-side setting with a range check (data parallel)
+    assert N.lib.ddn_set_reserved_sms(8) == 0 and N.lib.ddn_set_reserved_sms(0) == 0
+    assert N.lib.ddn_set_reserved_sms(-1) == -1 and N.lib.ddn_set_reserved_sms(1000) == -1
     with pytest.raises(N.DdnError):
         N.check(-1)
 
