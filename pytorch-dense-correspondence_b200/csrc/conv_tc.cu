@@ -12,8 +12,13 @@
 //   (both bf16) and issuing hi*hi + hi*lo + lo*hi into the same fp32 TMEM accumulator (3 MMAs per k-step);
 //   DDN_PRECISION_BF16 issues hi*hi only.
 // * Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one thread),
-//   warps 2-5 = epilogue (tcgen05.ld -> registers -> fp32 NHWC global, optional fused addend).
+//   warps 2-5 = epilogue (tcgen05.ld -> in-register 8x8 transpose -> whole 128-byte lines of fp32 NHWC global memory, fused
+//   addend / BatchNorm statistics / folded inference BatchNorm).
 //   smem ring of kStages {A_hi,A_lo,B_hi,B_lo} slots with full/empty mbarriers; tcgen05.commit frees slots.
+// * Kernels in this file: conv_tc_kernel (every conv, single CTA or CTA pair), conv64_halo_kernel / wgrad64_halo_kernel (the
+//   64-channel layer: resident weights, one halo tile per 8x16 pixels, taps read in place), wgrad_tc_kernel (weight gradient,
+//   pixels as the K dimension), operand preparation (stem patches, zero insertion, weight packs + their device-side validation).
+// * Every kernel starts with griddepcontrol.launch_dependents / .wait (programmatic dependent launch, common.cuh).
 //
 // Reference op replaced: nn.Conv2d via conv3x3 (PSD/vision/torchvision/models/resnet.py:20-37,45,48) and the
 // stride-1 1x1 downsample convs (resnet.py:210-214), plus their autograd data gradient.
