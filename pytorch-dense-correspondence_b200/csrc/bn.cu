@@ -10,7 +10,6 @@
 // mantissa bits -- what every conv reads anyway); the residual add reads the planes, the ReLU mask of a BatchNorm without
 // residual is recomputed from its own input, and column statistics are finalized by the last CTA of the kernel that
 // produced them (bn_stats.cuh) instead of by a second launch.  G > 1: per-group batch statistics (pair-batched step).
-#include <cstring>
 #include "conv.cuh"
 
 namespace ddn {
@@ -397,132 +396,6 @@ stem_pool_relu_bwd_kernel(const float* __restrict__ dyp, const uint8_t* __restri
   }
 }
 
-// ---- stem backward without the intermediate gradient: the max-pool / ReLU backward above writes g (315 MB for 16 images) only for
-// the BatchNorm backward to read it twice.  Here both BatchNorm passes gather g themselves (each conv-resolution pixel looks at the
-// <= 4 pooling windows it belongs to; dy_pool and the argmax bytes are 1/4 of the size and stay in L2):
-//   pass 1 (stem_bwd_colsum_kernel): column sums (sum g, sum g*xhat) per BatchNorm group -> dgamma, dbeta, sums (last CTA)
-//   pass 2 (stem_bwd_apply_kernel):  d raw = gamma*invstd*(g - sum g / M - xhat * sum(g*xhat) / M) -> the bf16 planes of the stem wgrad
-struct StemBwdArgs {
-  const float* dyp; const uint8_t* argmax; const float* x;
-  const float* mean; const float* invstd; const float* gamma; const float* beta;    // statistics [G][C]
-  __nv_bfloat16* dx_hi; __nv_bfloat16* dx_lo;
-  const float* sums;
-  int N, Hc, Wc, C, Hp, Wp, imgs_per_group, training;
-  int64_t rows_per_block;
-};
-
-// g of the channel quad c4 of conv-resolution pixel (n, h, w): sum over the pooling windows whose argmax is this pixel, times (bn(x) > 0)
-__device__ __forceinline__ float4 stem_gather_g(const StemBwdArgs& a, int n, int h, int w, int c4, const float4 v, const float4 mu,
-                                                const float4 sc, const float4 be) {
-  const int q = a.C >> 2;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int hp0 = h >> 1, hp1 = (h + 1) >> 1, wp0 = w >> 1, wp1 = (w + 1) >> 1;
-#pragma unroll
-  for (int u = 0; u < 2; ++u) {
-    const int hp = u ? hp1 : hp0;
-    if ((u && hp1 == hp0) || hp >= a.Hp) continue;
-    const int r = h - (2 * hp - 1);
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      const int wp = t ? wp1 : wp0;
-      if ((t && wp1 == wp0) || wp >= a.Wp) continue;
-      const int s = w - (2 * wp - 1);
-      const unsigned char k = (unsigned char)(r * 3 + s);
-      const int64_t pi = (((int64_t)n * a.Hp + hp) * a.Wp + wp) * q + c4;
-      const uchar4 am = __ldg(reinterpret_cast<const uchar4*>(a.argmax) + pi);
-      const float4 d = __ldg(reinterpret_cast<const float4*>(a.dyp) + pi);
-      if (am.x == k) acc.x += d.x;
-      if (am.y == k) acc.y += d.y;
-      if (am.z == k) acc.z += d.z;
-      if (am.w == k) acc.w += d.w;
-    }
-  }
-  if (!(fmaf(v.x - mu.x, sc.x, be.x) > 0.f)) acc.x = 0.f;
-  if (!(fmaf(v.y - mu.y, sc.y, be.y) > 0.f)) acc.y = 0.f;
-  if (!(fmaf(v.z - mu.z, sc.z, be.z) > 0.f)) acc.z = 0.f;
-  if (!(fmaf(v.w - mu.w, sc.w, be.w) > 0.f)) acc.w = 0.f;
-  return acc;
-}
-
-__global__ void __launch_bounds__(BN_THREADS)
-stem_bwd_colsum_kernel(StemBwdArgs a, BnBwdFinal fb) {
-  pdl_prologue();
-  const int C = a.C, q = C >> 2;
-  const int cq = threadIdx.x % q, rr = threadIdx.x / q, rpi = BN_THREADS / q;
-  const int g = blockIdx.y;
-  const int64_t Mg = (int64_t)a.imgs_per_group * a.Hc * a.Wc;
-  const int64_t r0 = (int64_t)g * Mg + (int64_t)blockIdx.x * a.rows_per_block;
-  const int64_t r1 = min((int64_t)(g + 1) * Mg, r0 + a.rows_per_block);
-  const float4 mu = reinterpret_cast<const float4*>(a.mean + (size_t)g * C)[cq];
-  const float4 is = reinterpret_cast<const float4*>(a.invstd + (size_t)g * C)[cq];
-  const float4 ga = reinterpret_cast<const float4*>(a.gamma)[cq];
-  const float4 be = reinterpret_cast<const float4*>(a.beta)[cq];
-  const float4 sc = make_float4(ga.x * is.x, ga.y * is.y, ga.z * is.z, ga.w * is.w);
-  float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
-  for (int64_t r = r0 + rr; r < r1; r += rpi) {
-    const int w = (int)(r % a.Wc); const int64_t t = r / a.Wc;
-    const int h = (int)(t % a.Hc), n = (int)(t / a.Hc);
-    const float4 v = __ldg(reinterpret_cast<const float4*>(a.x + r * C) + cq);
-    const float4 gr = stem_gather_g(a, n, h, w, cq, v, mu, sc, be);
-    s0.x += gr.x; s0.y += gr.y; s0.z += gr.z; s0.w += gr.w;
-    s1.x = fmaf(gr.x, (v.x - mu.x) * is.x, s1.x); s1.y = fmaf(gr.y, (v.y - mu.y) * is.y, s1.y);
-    s1.z = fmaf(gr.z, (v.z - mu.z) * is.z, s1.z); s1.w = fmaf(gr.w, (v.w - mu.w) * is.w, s1.w);
-  }
-  __shared__ float4 sh0[BN_THREADS], sh1[BN_THREADS];
-  __shared__ int s_last;
-  sh0[threadIdx.x] = s0; sh1[threadIdx.x] = s1;
-  __syncthreads();
-  if (rr == 0) {
-    for (int k = 1; k < rpi; ++k) {
-      const float4 u = sh0[k * q + cq], z = sh1[k * q + cq];
-      s0.x += u.x; s0.y += u.y; s0.z += u.z; s0.w += u.w;
-      s1.x += z.x; s1.y += z.y; s1.z += z.z; s1.w += z.w;
-    }
-    double* p0 = fb.a.acc + (size_t)(g * 2) * C + (cq << 2);
-    double* p1 = p0 + C;
-    red_add_f64(p0, (double)s0.x); red_add_f64(p0 + 1, (double)s0.y); red_add_f64(p0 + 2, (double)s0.z); red_add_f64(p0 + 3, (double)s0.w);
-    red_add_f64(p1, (double)s1.x); red_add_f64(p1 + 1, (double)s1.y); red_add_f64(p1 + 2, (double)s1.z); red_add_f64(p1 + 3, (double)s1.w);
-  }
-  const bool last = bn_last_cta(fb.a.ticket, gridDim.x * gridDim.y, threadIdx.x == 0, &s_last, [] { __syncthreads(); });
-  if (last)
-    for (int c = threadIdx.x; c < C; c += BN_THREADS) bn_bwd_finalize_channel(fb, c);
-}
-
-__global__ void __launch_bounds__(BN_THREADS)
-stem_bwd_apply_kernel(StemBwdArgs a) {
-  pdl_prologue();
-  const int C = a.C, q = C >> 2;
-  const int64_t Mg = (int64_t)a.imgs_per_group * a.Hc * a.Wc;
-  const float invM = (float)(1.0 / (double)Mg);
-  const int64_t total = (int64_t)a.N * a.Hc * a.Wc * q;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int cq = (int)(i % q); int64_t t = i / q;
-    const int w = (int)(t % a.Wc); t /= a.Wc;
-    const int h = (int)(t % a.Hc), n = (int)(t / a.Hc);
-    const int g = n / a.imgs_per_group;
-    const float4 mu = __ldg(reinterpret_cast<const float4*>(a.mean + (size_t)g * C) + cq);
-    const float4 is = __ldg(reinterpret_cast<const float4*>(a.invstd + (size_t)g * C) + cq);
-    const float4 ga = __ldg(reinterpret_cast<const float4*>(a.gamma) + cq);
-    const float4 be = __ldg(reinterpret_cast<const float4*>(a.beta) + cq);
-    const float4 k1 = make_float4(ga.x * is.x, ga.y * is.y, ga.z * is.z, ga.w * is.w);
-    float4 mb = make_float4(0.f, 0.f, 0.f, 0.f), mg = mb;
-    if (a.training) {
-      mb = __ldg(reinterpret_cast<const float4*>(a.sums + (size_t)(g * 2) * C) + cq);
-      mg = __ldg(reinterpret_cast<const float4*>(a.sums + (size_t)(g * 2 + 1) * C) + cq);
-      mb.x *= invM; mb.y *= invM; mb.z *= invM; mb.w *= invM;
-      mg.x *= invM; mg.y *= invM; mg.z *= invM; mg.w *= invM;
-    }
-    const float4 v = __ldg(reinterpret_cast<const float4*>(a.x) + i);
-    const float4 gr = stem_gather_g(a, n, h, w, cq, v, mu, k1, be);
-    float4 d;
-    d.x = k1.x * (gr.x - mb.x - (v.x - mu.x) * is.x * mg.x);
-    d.y = k1.y * (gr.y - mb.y - (v.y - mu.y) * is.y * mg.y);
-    d.z = k1.z * (gr.z - mb.z - (v.z - mu.z) * is.z * mg.z);
-    d.w = k1.w * (gr.w - mb.w - (v.w - mu.w) * is.w * mg.w);
-    store_split4(a.dx_hi, a.dx_lo, i, d);
-  }
-}
-
 // ------------------------------------------------------------------------------------------------ launchers
 static int check_c(int C, int G, int64_t M) {
   DDN_CHECK_ARG(C >= 4 && C % 4 == 0 && (C / 4) <= BN_THREADS && BN_THREADS % (C / 4) == 0,
@@ -616,27 +489,6 @@ int launch_stem_pool_relu_backward(const float* dy_pool, const uint8_t* argmax, 
   int64_t total = (int64_t)N * Hc * Wc * (C / 4);
   DDN_LAUNCH(stem_pool_relu_bwd_kernel, ew_blocks(stem_pool_relu_bwd_kernel, 0, total), 256, 0, st, dy_pool, argmax, x, mean, invstd, gamma, beta, g,
              N, Hc, Wc, C, Hp, Wp, N / G);
-  return 0;
-}
-
-// stem backward (tensor-core modes): dy_pool -> d raw conv1 as bf16 planes + dgamma / dbeta, without materialising g
-int launch_stem_backward_fused(const float* dy_pool, const uint8_t* argmax, const float* x, const float* mean, const float* invstd,
-                               const float* gamma, const float* beta, __nv_bfloat16* dx_hi, __nv_bfloat16* dx_lo, float* dgamma,
-                               float* dbeta, BnAccum acc, float* sums, int N, int Hc, int Wc, int C, int G, int training, cudaStream_t st) {
-  DDN_CHECK_ARG(dy_pool && argmax && x && mean && invstd && gamma && beta && dx_hi && dgamma && dbeta && sums, "stem backward: null tensor");
-  DDN_TRY(check_c(C, G, (int64_t)N * Hc * Wc));
-  StemBwdArgs a;
-  memset(&a, 0, sizeof(a));
-  a.dyp = dy_pool; a.argmax = argmax; a.x = x; a.mean = mean; a.invstd = invstd; a.gamma = gamma; a.beta = beta;
-  a.dx_hi = dx_hi; a.dx_lo = dx_lo; a.sums = sums;
-  a.N = N; a.Hc = Hc; a.Wc = Wc; a.C = C; a.Hp = (Hc - 1) / 2 + 1; a.Wp = (Wc - 1) / 2 + 1; a.imgs_per_group = N / G; a.training = training;
-  const int64_t Mg = (int64_t)(N / G) * Hc * Wc;
-  const int resident = resident_blocks(stem_bwd_colsum_kernel, 0);
-  a.rows_per_block = bn_colsum_rows_per_block(Mg, C, G, resident);
-  BnBwdFinal fb = {acc, sums, dgamma, dbeta, G, C};
-  dim3 grid((unsigned)bn_colsum_blocks(Mg, C, G, resident), (unsigned)G);
-  DDN_LAUNCH(stem_bwd_colsum_kernel, grid, BN_THREADS, 0, st, a, fb);
-  DDN_LAUNCH(stem_bwd_apply_kernel, ew_blocks(stem_bwd_apply_kernel, 0, (int64_t)N * Hc * Wc * (C / 4)), BN_THREADS, 0, st, a);
   return 0;
 }
 

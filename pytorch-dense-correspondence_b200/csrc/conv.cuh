@@ -71,11 +71,6 @@ int launch_stem_pool_relu_backward(const float* dy_pool, const uint8_t* argmax, 
                                    const float* invstd, const float* gamma, const float* beta, float* g,
                                    int N, int Hc, int Wc, int C, int G, cudaStream_t st);
 
-// the two passes of the stem's BatchNorm backward gather the max-pool / ReLU gradient themselves (no intermediate g tensor)
-int launch_stem_backward_fused(const float* dy_pool, const uint8_t* argmax, const float* x, const float* mean, const float* invstd,
-                               const float* gamma, const float* beta, __nv_bfloat16* dx_hi, __nv_bfloat16* dx_lo, float* dgamma,
-                               float* dbeta, BnAccum acc, float* sums, int N, int Hc, int Wc, int C, int G, int training, cudaStream_t st);
-
 // head.cu
 int launch_nchw_to_nhwc4(const float* x, float* y, int N, int H, int W, cudaStream_t st);
 // feat [N*Mimg][C]: fp32 (`feat`) or bf16 planes (feat = hi + lo) when feat == nullptr

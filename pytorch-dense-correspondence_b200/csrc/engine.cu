@@ -672,18 +672,6 @@ static int net_backward(const Ctx& c, const float* dy, const float* dlow_nhwc, d
   }
   // stem: maxpool -> relu -> bn1 -> conv1 (weight gradient only; the image is not differentiated)
   int t1 = (cur + 1) & 3, t2 = (cur + 2) & 3;
-  static const bool stem_fused = [] { const char* e = getenv("DDN_STEM_BWD_FUSED"); return !(e && e[0] == '0'); }();
-  if (p.tc && stem_fused) {
-    // tensor-core modes: the max-pool / ReLU gradient is never written; both BatchNorm passes gather it (bn.cu, stem backward)
-    DDN_TRY(launch_stem_backward_fused(S[cur], reinterpret_cast<const uint8_t*>(c.ws + p.argmax), c.f(p.stem_raw), c.mean(p.stem_stats),
-                                       c.invstd(p.stem_stats, 64), c.params + s.stem_bn.g_off, c.params + s.stem_bn.b_off,
-                                       c.h(p.grad_p.hi), want_lo ? c.h(p.grad_p.lo) : nullptr, c.grads + s.stem_bn.g_off,
-                                       c.grads + s.stem_bn.b_off, c.accum(), c.f(p.sums), B, p.H1, p.W1, 64, c.G, c.training() ? 1 : 0, c.st));
-    DDN_TRY(tc_stem_wgrad(c.planes(p.patch_p), c.planes(p.grad_p), nullptr, B, p.H1, p.W1, p.precision, c.f(p.dwp_all) + s.n_params, c.st));
-    TcUnpackEntry e; e.src_off = s.n_params; e.dst_off = s.stem.w_off; e.Cout = 64; e.Cin = 3; e.taps = 49; e.kind = 1;
-    pending.push_back(e);
-    return close_bucket(0);
-  }
   DDN_TRY(launch_stem_pool_relu_backward(S[cur], reinterpret_cast<const uint8_t*>(c.ws + p.argmax), c.f(p.stem_raw),
                                          c.mean(p.stem_stats), c.invstd(p.stem_stats, 64), c.params + s.stem_bn.g_off,
                                          c.params + s.stem_bn.b_off, S[t1], B, p.H1, p.W1, 64, c.G, c.st));
