@@ -24,7 +24,10 @@ constexpr int LR_THREADS = 128;      // small CTAs: the kernels are a single L2 
 // bilinear source cell + weights of output pixel (u, v): identical arithmetic to head.cu::src_index / upsample_fwd_kernel
 struct Blend { int c00, c01, c10, c11; float lh, lw; };
 __device__ __forceinline__ Blend blend_of(int64_t n, int W, int h, int w, float sh, float sw) {
-  const int v = (int)(n / W), u = (int)(n - (int64_t)v * W);
+  // 0 <= n < H * W < 2^31 (checked by the callers): a 32-bit division -- the 64-bit one is ~80 instructions, and these kernels are
+  // instruction-bound (ncu: issue slots 45 % / 65 % busy at C3, DRAM 7 % / 10 %)
+  const unsigned ni = (unsigned)n;
+  const int v = (int)(ni / (unsigned)W), u = (int)(ni - (unsigned)v * (unsigned)W);
   float r = sh * (float)v;
   int h0 = (int)r; if (h0 > h - 1) h0 = h - 1;
   const int h1 = h0 + ((h0 < h - 1) ? 1 : 0);
@@ -450,7 +453,7 @@ extern "C" int ddn_contrastive_terms_forward_lowres(const float* low_a, const fl
                                                     const ddn_loss_term* terms_host, int n_terms,
                                                     double* sums, int64_t* counts, void* stream) {
   DDN_TRY(check_common(low_a, low_b, B, (int64_t)H * W, D, W));
-  DDN_CHECK_ARG(sums && counts && h >= 1 && w >= 1 && H >= h && W >= w, "bad low-resolution geometry / null outputs");
+  DDN_CHECK_ARG(sums && counts && h >= 1 && w >= 1 && H >= h && W >= w && (int64_t)H * W < (1LL << 31), "bad low-resolution geometry / null outputs");
   const int lpp = (D == 8 || D == 16 || D == 32) ? D / 4 : 1;
   // 4 pairs per lane group; 8 (DDN_LOSS_FWD_ITEMS=8) halves the atomics again but costs occupancy: 17.4 -> 18.7-20.9 us at C3
   static const int items = [] { const char* e = getenv("DDN_LOSS_FWD_ITEMS"); return (e && atoi(e) == 8) ? 8 : 4; }();
@@ -490,7 +493,7 @@ extern "C" int ddn_contrastive_terms_backward_lowres(const float* low_a, const f
                                                      const float* coef, const float* upstream,
                                                      float* dlow_a, float* dlow_b, void* stream) {
   DDN_TRY(check_common(low_a, low_b, B, (int64_t)H * W, D, W));
-  DDN_CHECK_ARG(coef && dlow_a && dlow_b && h >= 1 && w >= 1 && H >= h && W >= w, "bad low-resolution geometry / null buffers");
+  DDN_CHECK_ARG(coef && dlow_a && dlow_b && h >= 1 && w >= 1 && H >= h && W >= w && (int64_t)H * W < (1LL << 31), "bad low-resolution geometry / null buffers");
   DDN_CHECK_ARG(((reinterpret_cast<uintptr_t>(dlow_a) | reinterpret_cast<uintptr_t>(dlow_b) | reinterpret_cast<uintptr_t>(low_a) | reinterpret_cast<uintptr_t>(low_b)) & 15) == 0,
                 "low-resolution maps and their gradients must be 16-byte aligned");
   const int lpp = (D == 8 || D == 16 || D == 32) ? D / 4 : 1;
